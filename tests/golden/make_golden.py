@@ -1,0 +1,97 @@
+"""Generate tests/golden/*.npz by running the REFERENCE'S OWN compiled solver (oracle/_ref).
+
+Run in the build container (where /root/reference exists and `python oracle/build_ref.py` has
+produced oracle/_ref):      python tests/golden/make_golden.py
+
+Each fixture holds the exact float32 inputs handed to ``richardson_lucy_MM``
+(lib/deconvolution.pyx:341) and what the unmodified reference returned / mutated: the output view,
+the full padded ``u``, the caller's ``psf`` array and the executed outer-iteration count.  The
+reference has no tests or golden vectors of its own; these fixtures are the pin.
+"""
+from __future__ import annotations
+
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+
+from image_cases_studies_b200 import synthetic  # noqa: E402
+from image_cases_studies_b200.lib import utils  # noqa: E402
+from oracle import ref_loader  # noqa: E402
+
+OUT = Path(__file__).resolve().parent
+
+
+def white_case(M, N, K, true_psf, blind, seed):
+    kt = utils.stack3(true_psf)
+    image, u0 = synthetic.make_inputs(M, N, kt, seed)
+    psf0 = utils.stack3(utils.uniform_kernel(K)) if blind else kt.copy()
+    return image, u0, psf0, synthetic.default_window(M, N, K // 2)
+
+
+def smooth_case(M, N, K, blind, seed, box=5):
+    """Box-smoothed scene + a little noise: the non-blind whiteness statistic turns around after ~20
+    outer iterations, so the reference's stop rule (lib/deconvolution.pyx:643-654) fires."""
+    rng = np.random.default_rng(seed)
+    p = K // 2
+    s = 0.1 + 0.8 * rng.random((M + 2 * p, N + 2 * p, 3), dtype=np.float32)
+    # separable box filter in plain numpy (no scipy.ndimage dependency)
+    ker = np.ones(box) / box
+    for ax in (0, 1):
+        s = np.apply_along_axis(lambda v: np.convolve(np.pad(v, box // 2, mode="reflect"), ker, mode="valid"), ax, s)
+    s = s.astype(np.float32)
+    kt = utils.stack3(utils.gaussian_kernel(K, K / 4))
+    image = synthetic._valid_conv_fft(s, kt)
+    image += (0.002 * rng.standard_normal(image.shape)).astype(np.float32)
+    u0 = np.ascontiguousarray(np.pad(image, ((p, p), (p, p), (0, 0)), mode="edge"))
+    psf0 = utils.stack3(utils.uniform_kernel(K)) if blind else kt
+    return image, u0, psf0, synthetic.default_window(M, N, p)
+
+
+CASES = {
+    # name: (builder, kwargs for the solver)
+    "nonblind_64x64_k5": (lambda: white_case(64, 64, 5, utils.gaussian_kernel(5, 1.0), False, 11),
+                          dict(tau=1.0, iterations=3, step_factor=1e-3, lambd=1e4, blind=False)),
+    "blind_72x80_k9": (lambda: white_case(72, 80, 9, utils.gaussian_kernel(9, 2.0), True, 12),
+                       dict(tau=0.0, iterations=4, step_factor=1e-3, lambd=1e4, blind=True)),
+    "blind_corr_64x72_k7": (lambda: white_case(64, 72, 7, utils.kaiser_kernel(7, 4.0), True, 13),
+                            dict(tau=0.0, iterations=3, step_factor=1e-3, lambd=1e4, blind=True, correlation=True)),
+    "blind_48x56_k3": (lambda: white_case(48, 56, 3, utils.gaussian_kernel(3, 0.8), True, 14),
+                       dict(tau=0.0, iterations=5, step_factor=5e-3, lambd=5e3, blind=True)),
+    "blind_80x64_k15": (lambda: white_case(80, 64, 15, utils.gaussian_kernel(15, 3.0), True, 15),
+                        dict(tau=0.0, iterations=2, step_factor=1e-3, lambd=1e4, blind=True)),
+    "nonblind_stop_80x96_k7": (lambda: smooth_case(80, 96, 7, False, 0),
+                               dict(tau=0.0, iterations=30, step_factor=1e-3, lambd=1e4, blind=False)),
+    "nonblind_stop2_80x96_k7": (lambda: smooth_case(80, 96, 7, False, 1),
+                                dict(tau=0.0, iterations=30, step_factor=1e-3, lambd=1e4, blind=False)),
+}
+
+
+def main():
+    mod = ref_loader.load()
+    if mod is None:
+        sys.exit("oracle/_ref missing: run python oracle/build_ref.py first")
+    for name, (builder, kw) in CASES.items():
+        image, u0, psf0, window = builder()
+        out, u, psf, log = ref_loader.run(image, u0, psf0, window, kw["tau"], kw["iterations"], kw["step_factor"],
+                                          kw["lambd"], kw["blind"], kw.get("correlation", False))
+        its = ref_loader.executed_iterations(log)
+        np.savez_compressed(OUT / f"{name}.npz", image=image, u0=u0, psf0=psf0, window=np.array(window),
+                            tau=kw["tau"], iterations=kw["iterations"], step_factor=kw["step_factor"],
+                            lambd=kw["lambd"], blind=kw["blind"], correlation=kw.get("correlation", False),
+                            ref_out=np.ascontiguousarray(out), ref_u=u, ref_psf=psf, ref_iterations=its)
+        print(f"{name}: executed {its}/{kw['iterations']} outer iterations, out {out.shape}")
+    # normalize_kernel (lib/deconvolution.pyx:73-75) on a kernel with negative taps
+    rng = np.random.default_rng(21)
+    kern = (rng.random((7, 7, 3), dtype=np.float32) - 0.3).astype(np.float32)
+    ref = kern.copy()
+    mod.normalize_kernel(ref, 7)
+    np.savez_compressed(OUT / "normalize_kernel_k7.npz", kern=kern, ref=ref)
+    print("normalize_kernel_k7: done")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,86 @@
+"""CPU tests: the numpy oracle (oracle/rl_mm_oracle.py) is pinned to the reference's compiled solver.
+
+* against the committed golden vectors (tests/golden/*.npz, produced by tests/golden/make_golden.py
+  from the unmodified /root/reference/lib/deconvolution.pyx), always;
+* against oracle/_ref run live, when the built reference module is present.
+"""
+import numpy as np
+import pytest
+
+from helpers import TOL_IMAGE_REL_L2, TOL_PSF_L1, golden_names, load_golden, psf_l1, rel_l2
+from oracle import ref_loader
+from oracle import rl_mm_oracle as orc
+
+
+def _run_oracle(g, dtype=np.float64):
+    M, N = g["image"].shape[:2]
+    MK = g["psf0"].shape[0]
+    return orc.richardson_lucy_MM(g["image"], g["u0"], g["psf0"], *g["window"], g["tau"], M, N, 3, MK,
+                                  g["iterations"], g["step_factor"], g["lambd"], blind=g["blind"],
+                                  correlation=g["correlation"], dtype=dtype)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_oracle_matches_golden(name):
+    g = load_golden(name)
+    r = _run_oracle(g)
+    # The stop test (lib/deconvolution.pyx:643-654) compares float32 statistics; where the reference
+    # stopped early on float32 noise (relative step of M_r below 1e-5) the count cannot be reproduced.
+    if r.iterations != g["ref_iterations"]:
+        k = min(r.iterations, g["ref_iterations"]) - 1
+        margin = abs(r.M_r[k] - r.M_r[k - 1]) / r.M_r[k]
+        assert margin < 1e-5, f"iteration count {r.iterations} != {g['ref_iterations']} with margin {margin:.2e}"
+        pytest.skip(f"reference stopped on float32 noise (margin {margin:.1e}); outputs not comparable")
+    assert rel_l2(r.out, g["ref_out"]) <= 2e-6           # measured ~2e-7: float32 noise of the reference
+    assert rel_l2(r.u, g["ref_u"]) <= 2e-6
+    assert psf_l1(r.psf_caller, g["ref_psf"]) <= 1e-5    # measured ~1e-6
+    assert rel_l2(r.out, g["ref_out"]) <= TOL_IMAGE_REL_L2 and psf_l1(r.psf_caller, g["ref_psf"]) <= TOL_PSF_L1
+
+
+def test_oracle_float32_mode_close_to_float64():
+    g = load_golden("blind_72x80_k9")
+    a, b = _run_oracle(g, np.float64), _run_oracle(g, np.float32)
+    assert a.iterations == b.iterations
+    assert rel_l2(b.out, a.out) < 5e-6 and psf_l1(b.psf, a.psf) < 1e-5
+
+
+def test_normalize_kernel_golden():
+    z = np.load(__import__("helpers").GOLDEN / "normalize_kernel_k7.npz")
+    k = z["kern"].astype(np.float64)
+    orc.normalize_kernel(k)
+    assert np.abs(k - z["ref"]).max() < 1e-6
+    assert np.allclose(k.sum(axis=(0, 1)), 1.0) and k.min() >= 0
+
+
+def test_conv_modes_against_direct_definition():
+    rng = np.random.default_rng(0)
+    a = rng.random((11, 13))
+    b = rng.random((3, 5))
+    assert np.allclose(orc.conv2(a, b, "valid"), orc.conv2_valid_direct(a, b), atol=1e-12)
+    full = orc.conv2(a, b, "full")
+    assert full.shape == (13, 17)
+    assert np.allclose(full[2:-2, 4:-4], orc.conv2_valid_direct(a, b), atol=1e-12)
+    same = orc.conv2(a, rng.random((11, 13)), "same")
+    assert same.shape == a.shape
+
+
+def test_whiteness_weights_normalised():
+    w = orc.whiteness_weights(31, 37)
+    assert w.shape == (31, 37) and abs(w.sum() - 1) < 1e-12 and w[15, 18] == w.max()
+
+
+@pytest.mark.skipif(ref_loader.so_path() is None, reason="oracle/_ref not built")
+@pytest.mark.parametrize("blind,K,shape", [(False, 5, (96, 112)), (True, 7, (90, 84)), (True, 11, (100, 100))])
+def test_oracle_matches_live_reference(blind, K, shape):
+    from image_cases_studies_b200 import synthetic
+    from image_cases_studies_b200.lib import utils
+
+    kt = utils.stack3(utils.gaussian_kernel(K, K / 4))
+    image, u0 = synthetic.make_inputs(*shape, kt, seed=100 + K)
+    psf0 = utils.stack3(utils.uniform_kernel(K)) if blind else kt
+    win = synthetic.default_window(*shape, K // 2)
+    tau = 0.0 if blind else 1.0
+    out, u, psf, log = ref_loader.run(image, u0, psf0, win, tau, 3, 1e-3, 1e4, blind)
+    r = orc.richardson_lucy_MM(image, u0, psf0, *win, tau, *shape, 3, K, 3, 1e-3, 1e4, blind=blind)
+    assert ref_loader.executed_iterations(log) == r.iterations == 3
+    assert rel_l2(r.out, out) <= 2e-6 and psf_l1(r.psf, psf) <= 1e-5
