@@ -1,0 +1,90 @@
+"""ctypes binding of the C ABI in include/rltv_b200.h (csrc/ -> librltv_b200.so).
+
+There is no fallback: if the shared library is missing, importing this module raises ImportError;
+if no CUDA device is present every compute call raises RuntimeError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "librltv_b200.so"
+
+RLTV_MAX_HISTORY = 4096
+RLTV_MAX_MK = 31
+INNER_ITER = 5
+
+
+class Params(C.Structure):
+    _fields_ = [("top", C.c_int32), ("bottom", C.c_int32), ("left", C.c_int32), ("right", C.c_int32),
+                ("tau", C.c_float), ("iterations", C.c_int32), ("step_factor", C.c_float), ("lambd", C.c_float),
+                ("blind", C.c_int32), ("correlation", C.c_int32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("iterations_executed", C.c_int32), ("stopped", C.c_int32), ("M_r", C.c_float),
+                ("M_r_prev", C.c_float), ("dt", C.c_float * 3), ("dtpsf", C.c_float), ("solve_ms", C.c_float),
+                ("kernel_launches", C.c_int32), ("n_history", C.c_int32),
+                ("M_r_history", C.c_float * RLTV_MAX_HISTORY)]
+
+    def as_dict(self):
+        return dict(iterations=int(self.iterations_executed), stopped=bool(self.stopped), M_r=float(self.M_r),
+                    M_r_prev=float(self.M_r_prev), dt=tuple(float(x) for x in self.dt), dtpsf=float(self.dtpsf),
+                    solve_ms=float(self.solve_ms), kernel_launches=int(self.kernel_launches),
+                    M_r_history=[float(self.M_r_history[i]) for i in range(int(self.n_history))])
+
+
+# every symbol include/rltv_b200.h declares: (name, restype, argtypes)
+_FP = C.POINTER(C.c_float)
+SYMBOLS = [
+    ("rltv_abi_version", C.c_int, []),
+    ("rltv_last_error", C.c_char_p, []),
+    ("rltv_device_count", C.c_int, []),
+    ("rltv_richardson_lucy_mm", C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int32,
+                                          C.c_int32, C.c_int32, C.POINTER(Params), C.POINTER(Stats), C.c_void_p, C.c_int32]),
+    ("rltv_normalize_kernel", C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
+    ("rltv_create", C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    ("rltv_destroy", C.c_int, [C.c_void_p]),
+    ("rltv_upload", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
+    ("rltv_download", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    ("rltv_solve", C.c_int, [C.c_void_p, C.POINTER(Params), C.POINTER(Stats)]),
+    ("rltv_begin", C.c_int, [C.c_void_p, C.POINTER(Params)]),
+    ("rltv_enqueue_outer", C.c_int, [C.c_void_p, C.c_int32]),
+    ("rltv_finish", C.c_int, [C.c_void_p, C.POINTER(Stats)]),
+    ("rltv_stream", C.c_void_p, [C.c_void_p]),
+    ("rltv_profile_enable", C.c_int, [C.c_void_p, C.c_int32]),
+    ("rltv_profile_get", C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
+    ("rltv_stage_residual", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("rltv_stage_adjoint", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("rltv_stage_gradk", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("rltv_stage_whiteness", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float)]),
+]
+
+if not LIB_PATH.exists():
+    raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                      "(nvcc, sm_100a). There is no CPU fallback.")
+lib = C.CDLL(str(LIB_PATH))
+for _name, _res, _args in SYMBOLS:
+    _fn = getattr(lib, _name)
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+def last_error() -> str:
+    return (lib.rltv_last_error() or b"").decode()
+
+
+def check(rc: int):
+    if rc == 0:
+        return
+    msg = last_error()
+    if rc == -1:
+        raise ValueError(msg)
+    raise RuntimeError(f"rltv error {rc}: {msg}")
+
+
+def ptr(a: np.ndarray):
+    return C.c_void_p(a.ctypes.data)

@@ -1,0 +1,703 @@
+// Host side of the C ABI declared in include/rltv_b200.h: context, buffers, launch sequencing.
+// One inner step of the reference (lib/deconvolution.pyx:473-591) is the kernel sequence
+//   k_conv_fwd -> k_conv_adj -> k_update [-> k_conv_fwd -> k_gradk -> k_gradk_reduce -> k_psf_update]
+// and one outer iteration (pyx:460-656) is  ut=u ; 5 inner steps ; whiteness statistic + stop rule.
+// Nothing is read back between kernels: step sizes, the PSF, the statistic and the stop flag live in a
+// device-resident State; once the flag is set every later kernel returns at its first instruction, so the
+// host may run ahead (it polls the flag two outer iterations behind, without draining the stream).
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/rltv_b200.h"
+#include "rltv_common.cuh"
+#include "rltv_elementwise.cuh"
+#include "rltv_stencil.cuh"
+#include "rltv_whiteness.cuh"
+
+using namespace rltv;
+
+namespace {
+
+thread_local std::string g_err;
+constexpr int NCH = 64;  // chunks of the cross-tile PSF-gradient reduction
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CU(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t e_ = (call);                                                                      \
+    if (e_ != cudaSuccess)                                                                        \
+      return fail(RLTV_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));             \
+  } while (0)
+
+enum Family { F_CONV_FWD = 0, F_CONV_ADJ, F_UPDATE, F_GRADK, F_PSF, F_STATS, F_COPY, F_COUNT };
+const char* kFamilyNames[F_COUNT] = {"conv_fwd", "conv_adj", "update", "gradk", "psf", "stats", "copy"};
+
+}  // namespace
+
+struct rltv_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  Geom g{};
+  float *u = nullptr, *ut = nullptr, *gbuf = nullptr, *img = nullptr, *err = nullptr;
+  float* staging = nullptr;
+  float *psf = nullptr, *psf_caller = nullptr, *psf_hwc = nullptr;
+  State* st = nullptr;
+  State* h_st = nullptr;        // pinned mirror
+  int* h_poll = nullptr;        // pinned ring: {stop, it} per slot
+  cudaEvent_t poll_ev[4]{};
+  float* gk_partial = nullptr;
+  int gk_ntiles = 0;
+  double* gk_partial2 = nullptr;
+  float* gk_out = nullptr;
+  // whiteness
+  WhiteGeom wg{};
+  double2 *Z = nullptr, *tw = nullptr;
+  double *wa = nullptr, *wb = nullptr, *rowacc = nullptr, *rowsum = nullptr;
+  float *rowmin = nullptr, *rowmax = nullptr, *mr_out = nullptr;
+  int wcap_L = 0, wcap_h = 0, wcap_w = 0;
+  rltv_params_t params{};
+  bool uploaded = false, begun = false;
+  int outer_enqueued = 0;
+  long launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // profiling
+  bool prof = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev[F_COUNT];
+  size_t prof_used[F_COUNT]{};
+  float prof_ms[F_COUNT]{};
+  int prof_n[F_COUNT]{};
+};
+
+namespace {
+
+struct ProfScope {
+  rltv_ctx* c;
+  int fam;
+  cudaEvent_t stop = nullptr;
+  ProfScope(rltv_ctx* ctx, int f) : c(ctx), fam(f) {
+    c->launches++;
+    if (!c->prof) return;
+    auto& pool = c->prof_ev[fam];
+    if (c->prof_used[fam] == pool.size()) {
+      cudaEvent_t a, b;
+      cudaEventCreate(&a);
+      cudaEventCreate(&b);
+      pool.emplace_back(a, b);
+    }
+    auto& p = pool[c->prof_used[fam]++];
+    cudaEventRecord(p.first, c->stream);
+    stop = p.second;
+  }
+  ~ProfScope() {
+    if (stop) cudaEventRecord(stop, c->stream);
+  }
+};
+
+void prof_collect(rltv_ctx* c) {
+  for (int f = 0; f < F_COUNT; ++f) {
+    for (size_t i = 0; i < c->prof_used[f]; ++i) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, c->prof_ev[f][i].first, c->prof_ev[f][i].second) == cudaSuccess) {
+        c->prof_ms[f] += ms;
+        c->prof_n[f] += 1;
+      }
+    }
+    c->prof_used[f] = 0;
+  }
+}
+
+// ---- K-dispatch ------------------------------------------------------------------------------------
+#define RLTV_FOR_EACH_K(M) \
+  M(3) M(5) M(7) M(9) M(11) M(13) M(15) M(17) M(19) M(21) M(23) M(25) M(27) M(29) M(31)
+
+template <int K>
+int launch_conv_fwd_t(rltv_ctx* c) {
+  using C = ConvCfg<K>;
+  static bool attr = false;
+  if (!attr) {
+    CU(cudaFuncSetAttribute(k_conv_fwd<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(C::SMEM_BYTES)));
+    attr = true;
+  }
+  dim3 grid((c->g.pitch + C::TW - 1) / C::TW, (c->g.Hu + C::TH - 1) / C::TH, 3);
+  ProfScope p(c, F_CONV_FWD);
+  k_conv_fwd<K><<<grid, C::THREADS, C::SMEM_BYTES, c->stream>>>(c->g, c->st, c->u, c->img, c->psf, c->err);
+  return RLTV_OK;
+}
+
+template <int K>
+int launch_conv_adj_t(rltv_ctx* c, float lambd) {
+  using C = ConvCfg<K>;
+  static bool attr = false;
+  if (!attr) {
+    CU(cudaFuncSetAttribute(k_conv_adj<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(C::SMEM_BYTES)));
+    attr = true;
+  }
+  dim3 grid((c->g.pitch + C::TW - 1) / C::TW, (c->g.Hu + C::TH - 1) / C::TH, 3);
+  ProfScope p(c, F_CONV_ADJ);
+  k_conv_adj<K><<<grid, C::THREADS, C::SMEM_BYTES, c->stream>>>(c->g, c->st, c->err, c->psf, c->u, c->ut, lambd, c->gbuf);
+  return RLTV_OK;
+}
+
+template <int K>
+void gradk_grid_t(const Geom& g, int* gx, int* gy) {
+  using C = GradkCfg<K>;
+  *gx = (g.Wu + C::TW - 1) / C::TW;
+  *gy = (g.Hu + C::TH - 1) / C::TH;
+}
+
+template <int K>
+int launch_gradk_t(rltv_ctx* c) {
+  using C = GradkCfg<K>;
+  static bool attr = false;
+  if (!attr) {
+    CU(cudaFuncSetAttribute(k_gradk<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(C::SMEM_BYTES)));
+    attr = true;
+  }
+  int gx, gy;
+  gradk_grid_t<K>(c->g, &gx, &gy);
+  dim3 grid(gx, gy, 3 * C::NCHUNK);
+  {
+    ProfScope p(c, F_GRADK);
+    k_gradk<K><<<grid, C::THREADS, C::SMEM_BYTES, c->stream>>>(c->g, c->st, c->err, c->u, c->gk_partial);
+  }
+  {
+    ProfScope p(c, F_GRADK);
+    k_gradk_reduce<NCH><<<dim3(NCH, 3), 256, 0, c->stream>>>(c->st, c->gk_partial, gx * gy, K * K, c->gk_partial2);
+  }
+  return RLTV_OK;
+}
+
+int launch_conv_fwd(rltv_ctx* c) {
+  switch (c->g.K) {
+#define M(K_) case K_: return launch_conv_fwd_t<K_>(c);
+    RLTV_FOR_EACH_K(M)
+#undef M
+  }
+  return fail(RLTV_ERR_ARG, "unsupported MK");
+}
+int launch_conv_adj(rltv_ctx* c, float lambd) {
+  switch (c->g.K) {
+#define M(K_) case K_: return launch_conv_adj_t<K_>(c, lambd);
+    RLTV_FOR_EACH_K(M)
+#undef M
+  }
+  return fail(RLTV_ERR_ARG, "unsupported MK");
+}
+int launch_gradk(rltv_ctx* c) {
+  switch (c->g.K) {
+#define M(K_) case K_: return launch_gradk_t<K_>(c);
+    RLTV_FOR_EACH_K(M)
+#undef M
+  }
+  return fail(RLTV_ERR_ARG, "unsupported MK");
+}
+int gradk_ntiles(const Geom& g) {
+  int gx = 0, gy = 0;
+  switch (g.K) {
+#define M(K_) case K_: gradk_grid_t<K_>(g, &gx, &gy); break;
+    RLTV_FOR_EACH_K(M)
+#undef M
+  }
+  return gx * gy;
+}
+
+int launch_update(rltv_ctx* c) {
+  dim3 grid((c->g.pitch / 4 + 255) / 256, c->g.Hu, 3);
+  ProfScope p(c, F_UPDATE);
+  k_update<<<grid, 256, 0, c->stream>>>(c->g, c->st, c->u, c->ut, c->gbuf, c->img, c->params.step_factor,
+                                        c->params.lambd, c->params.blind);
+  return RLTV_OK;
+}
+
+int launch_psf_update(rltv_ctx* c) {
+  const int K = c->g.K;
+  ProfScope p(c, F_PSF);
+  k_psf_update<NCH><<<1, 256, 6 * K * K * sizeof(float), c->stream>>>(c->st, c->gk_partial2, K, c->params.step_factor,
+                                                                     c->params.correlation, c->psf, c->psf_caller);
+  return RLTV_OK;
+}
+
+int next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+// (Re)allocate the whiteness buffers for a window and upload twiddles / separable weights.
+int setup_whiteness(rltv_ctx* c, int top, int bottom, int left, int right) {
+  const int h = bottom - top, w = right - left;
+  if (top < 0 || left < 0 || bottom > c->g.M || right > c->g.N || h < 2 || w < 2)
+    return fail(RLTV_ERR_ARG, "whiteness window outside the image");
+  const int mx = h > w ? h : w;
+  int L = next_pow2(mx + (mx + 1) / 2 + 1);
+  if (L < 64) L = 64;
+  if (L > 2048) return fail(RLTV_ERR_ARG, "whiteness window larger than 1364 pixels is not supported");
+  int log2L = 0;
+  while ((1 << log2L) < L) ++log2L;
+  if (L > c->wcap_L) {
+    cudaFree(c->Z); cudaFree(c->tw);
+    CU(cudaMalloc(&c->Z, size_t(3) * L * L * sizeof(double2)));
+    CU(cudaMalloc(&c->tw, size_t(L / 2) * sizeof(double2)));
+    c->wcap_L = L;
+  }
+  if (h > c->wcap_h || w > c->wcap_w) {
+    cudaFree(c->wa); cudaFree(c->wb); cudaFree(c->rowacc); cudaFree(c->rowsum); cudaFree(c->rowmin); cudaFree(c->rowmax);
+    const int ch = h > c->wcap_h ? h : c->wcap_h, cw = w > c->wcap_w ? w : c->wcap_w;
+    CU(cudaMalloc(&c->wa, ch * sizeof(double)));
+    CU(cudaMalloc(&c->wb, cw * sizeof(double)));
+    CU(cudaMalloc(&c->rowacc, 3 * ch * sizeof(double)));
+    CU(cudaMalloc(&c->rowsum, 3 * ch * sizeof(double)));
+    CU(cudaMalloc(&c->rowmin, 3 * ch * sizeof(float)));
+    CU(cudaMalloc(&c->rowmax, 3 * ch * sizeof(float)));
+    c->wcap_h = ch; c->wcap_w = cw;
+  }
+  if (!c->mr_out) CU(cudaMalloc(&c->mr_out, sizeof(float)));
+  std::vector<double2> tw(L / 2);
+  for (int k = 0; k < L / 2; ++k) {
+    const double a = -2.0 * M_PI * double(k) / double(L);
+    tw[k] = make_double2(cos(a), sin(a));
+  }
+  // separable weights: W[n][m] = sqrt(gw(x_n) gw(x_m)) / sum  (pyx:35-36, :393-404); x = float32 linspace(-1, 1)
+  auto weights = [](int n) {
+    std::vector<double> v(n);
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) {
+      const double step = 2.0 / double(n - 1);
+      const float x = float(-1.0 + step * i);
+      const double gw = exp(-double(x) * double(x) / 2.0) / sqrt(2.0 * M_PI);
+      v[i] = sqrt(gw);
+      s += v[i];
+    }
+    for (auto& e : v) e /= s;
+    return v;
+  };
+  std::vector<double> wa = weights(h), wb = weights(w);
+  CU(cudaMemcpyAsync(c->tw, tw.data(), tw.size() * sizeof(double2), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->wa, wa.data(), h * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->wb, wb.data(), w * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));  // host vectors go out of scope
+  c->wg = WhiteGeom{top, left, h, w, L, log2L};
+  return RLTV_OK;
+}
+
+int launch_whiteness(rltv_ctx* c, int advance) {
+  const WhiteGeom& wg = c->wg;
+  const int L = wg.L;
+  const int fft_threads = L / 2 < 32 ? 32 : L / 2;
+  const size_t fft_smem = size_t(L) * sizeof(double2);
+  static bool attr = false;
+  if (!attr) {
+    CU(cudaFuncSetAttribute(k_white_rows_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * 16));
+    CU(cudaFuncSetAttribute(k_white_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * 16));
+    CU(cudaFuncSetAttribute(k_white_rows_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * 16));
+    attr = true;
+  }
+  { ProfScope p(c, F_STATS);
+    k_win_rows<<<dim3(wg.h, 3), 128, 0, c->stream>>>(c->g, c->st, c->err, wg, c->rowsum, c->rowmin, c->rowmax); }
+  { ProfScope p(c, F_STATS);
+    k_win_final<<<1, 256, 0, c->stream>>>(c->st, wg, c->rowsum, c->rowmin, c->rowmax); }
+  { ProfScope p(c, F_STATS);
+    k_white_rows_fwd<<<dim3(wg.h, 3), fft_threads, fft_smem, c->stream>>>(c->g, c->st, c->err, wg, c->tw, c->Z); }
+  { ProfScope p(c, F_STATS);
+    k_white_cols<<<dim3(L, 3), fft_threads, fft_smem, c->stream>>>(c->st, wg, c->tw, c->Z); }
+  { ProfScope p(c, F_STATS);
+    k_white_rows_inv<<<dim3(wg.h, 3), fft_threads, fft_smem, c->stream>>>(c->st, wg, c->tw, c->Z, c->wa, c->wb, c->rowacc); }
+  { ProfScope p(c, F_STATS);
+    k_outer_finalize<<<1, 32, 0, c->stream>>>(c->st, wg, c->rowacc, c->params.blind, c->params.tau, advance, c->mr_out); }
+  return RLTV_OK;
+}
+
+int enqueue_inner(rltv_ctx* c) {
+  int rc;
+  if ((rc = launch_conv_fwd(c)) != RLTV_OK) return rc;                    // pyx:477-488
+  if ((rc = launch_conv_adj(c, c->params.lambd)) != RLTV_OK) return rc;   // pyx:490-491, :519, :524
+  if ((rc = launch_update(c)) != RLTV_OK) return rc;                      // pyx:527-531, :499-502, :552
+  if (c->params.blind) {
+    if ((rc = launch_conv_fwd(c)) != RLTV_OK) return rc;                  // pyx:557-565
+    if ((rc = launch_gradk(c)) != RLTV_OK) return rc;                     // pyx:567-571
+    if ((rc = launch_psf_update(c)) != RLTV_OK) return rc;                // pyx:574-589
+  }
+  return RLTV_OK;
+}
+
+int enqueue_outer(rltv_ctx* c) {
+  {
+    ProfScope p(c, F_COPY);                                               // ut[:] = u.copy(), pyx:462
+    CU(cudaMemcpyAsync(c->ut, c->u, 3 * c->g.plane * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+  }
+  for (int i = 0; i < RLTV_INNER_ITER; ++i) {
+    int rc = enqueue_inner(c);
+    if (rc != RLTV_OK) return rc;
+  }
+  int rc = launch_whiteness(c, 1);
+  if (rc != RLTV_OK) return rc;
+  CU(cudaGetLastError());
+  return RLTV_OK;
+}
+
+void fill_stats(rltv_ctx* c, rltv_stats_t* s, float ms) {
+  if (!s) return;
+  const State& h = *c->h_st;
+  s->iterations_executed = h.it;
+  s->stopped = h.stop;
+  s->M_r = h.M_r;
+  s->M_r_prev = h.M_r_prev;
+  for (int i = 0; i < 3; ++i) s->dt[i] = h.dt[i];
+  s->dtpsf = h.dtpsf;
+  s->solve_ms = ms;
+  s->kernel_launches = int(c->launches);
+  s->n_history = h.n_hist;
+  std::memcpy(s->M_r_history, h.hist, sizeof(float) * (h.n_hist > 0 ? h.n_hist : 0));
+}
+
+int check_ctx(rltv_ctx* c) {
+  if (!c) return fail(RLTV_ERR_ARG, "null context");
+  CU(cudaSetDevice(c->device));
+  return RLTV_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+int rltv_abi_version(void) { return RLTV_ABI_VERSION; }
+const char* rltv_last_error(void) { return g_err.c_str(); }
+
+int rltv_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) {
+    cudaGetLastError();
+    return 0;
+  }
+  if (e != cudaSuccess) return fail(RLTV_ERR_CUDA, cudaGetErrorString(e));
+  return n;
+}
+
+int rltv_create(rltv_ctx** out, int32_t device, int32_t M, int32_t N, int32_t MK, void* stream) {
+  if (!out) return fail(RLTV_ERR_ARG, "null out pointer");
+  *out = nullptr;
+  if (MK < 3 || (MK % 2) == 0 || MK > RLTV_MAX_MK) return fail(RLTV_ERR_ARG, "MK must be odd and in [3, 31]");
+  if (M < 1 || N < 1) return fail(RLTV_ERR_ARG, "empty image");
+  if (M + MK - 1 > 65535) return fail(RLTV_ERR_ARG, "more than 65535 padded rows");
+  int ndev = rltv_device_count();
+  if (ndev <= 0) return fail(RLTV_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(RLTV_ERR_ARG, "bad device index");
+  CU(cudaSetDevice(device));
+  rltv_ctx* c = new rltv_ctx();
+  c->device = device;
+  if (stream) {
+    c->stream = reinterpret_cast<cudaStream_t>(stream);
+  } else {
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = true;
+  }
+  Geom& g = c->g;
+  g.M = M; g.N = N; g.K = MK; g.P = MK / 2;
+  g.Hu = M + MK - 1; g.Wu = N + MK - 1;
+  g.pitch = (g.Wu + 3) & ~3;
+  g.plane = size_t(g.Hu) * g.pitch;
+  const size_t pb = 3 * g.plane * sizeof(float);
+  float** planes[5] = {&c->u, &c->ut, &c->gbuf, &c->img, &c->err};
+  for (auto p : planes) {
+    if (cudaMalloc(p, pb) != cudaSuccess) { rltv_destroy(c); return fail(RLTV_ERR_ALLOC, "cudaMalloc of a frame plane set failed"); }
+    CU(cudaMemsetAsync(*p, 0, pb, c->stream));
+  }
+  CU(cudaMalloc(&c->staging, size_t(g.Hu) * g.Wu * 3 * sizeof(float)));
+  const size_t kb = size_t(3) * MK * MK * sizeof(float);
+  CU(cudaMalloc(&c->psf, kb));
+  CU(cudaMalloc(&c->psf_caller, kb));
+  CU(cudaMalloc(&c->psf_hwc, kb));
+  CU(cudaMalloc(&c->gk_out, kb));
+  CU(cudaMalloc(&c->st, sizeof(State)));
+  CU(cudaMemsetAsync(c->st, 0, sizeof(State), c->stream));
+  CU(cudaMallocHost(&c->h_st, sizeof(State)));
+  CU(cudaMallocHost(&c->h_poll, 4 * 2 * sizeof(int)));
+  for (auto& e : c->poll_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  CU(cudaEventCreate(&c->ev0));
+  CU(cudaEventCreate(&c->ev1));
+  c->gk_ntiles = gradk_ntiles(g);
+  CU(cudaMalloc(&c->gk_partial, size_t(3) * c->gk_ntiles * MK * MK * sizeof(float)));
+  CU(cudaMalloc(&c->gk_partial2, size_t(3) * NCH * MK * MK * sizeof(double)));
+  CU(cudaStreamSynchronize(c->stream));
+  *out = c;
+  return RLTV_OK;
+}
+
+int rltv_destroy(rltv_ctx* c) {
+  if (!c) return RLTV_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  float* f[] = {c->u, c->ut, c->gbuf, c->img, c->err, c->staging, c->psf, c->psf_caller, c->psf_hwc, c->gk_out,
+                c->gk_partial, c->rowmin, c->rowmax, c->mr_out};
+  for (auto p : f) cudaFree(p);
+  double* d[] = {c->gk_partial2, c->wa, c->wb, c->rowacc, c->rowsum};
+  for (auto p : d) cudaFree(p);
+  cudaFree(c->Z); cudaFree(c->tw); cudaFree(c->st);
+  if (c->h_st) cudaFreeHost(c->h_st);
+  if (c->h_poll) cudaFreeHost(c->h_poll);
+  for (auto& e : c->poll_ev) if (e) cudaEventDestroy(e);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  for (auto& pool : c->prof_ev) for (auto& p : pool) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return RLTV_OK;
+}
+
+void* rltv_stream(rltv_ctx* c) { return c ? reinterpret_cast<void*>(c->stream) : nullptr; }
+
+int rltv_upload(rltv_ctx* c, const float* image, size_t image_rs, const float* u, size_t u_rs, const float* psf) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  const Geom& g = c->g;
+  if (image) {
+    if (image_rs < size_t(g.N) * 12) return fail(RLTV_ERR_ARG, "image row stride smaller than a packed row");
+    CU(cudaMemcpy2DAsync(c->staging, size_t(g.N) * 12, image, image_rs, size_t(g.N) * 12, g.M, cudaMemcpyHostToDevice, c->stream));
+    k_hwc_to_planar<<<dim3((g.N * 3 + 255) / 256 > 64 ? 64 : (g.N * 3 + 255) / 256, g.M), 256, 0, c->stream>>>(
+        c->staging, size_t(g.N) * 3, g.M, g.N, c->img, g, g.P, g.P);
+    c->launches++;
+  }
+  if (u) {
+    if (u_rs < size_t(g.Wu) * 12) return fail(RLTV_ERR_ARG, "u row stride smaller than a packed row");
+    CU(cudaMemcpy2DAsync(c->staging, size_t(g.Wu) * 12, u, u_rs, size_t(g.Wu) * 12, g.Hu, cudaMemcpyHostToDevice, c->stream));
+    k_hwc_to_planar<<<dim3((g.Wu * 3 + 255) / 256 > 64 ? 64 : (g.Wu * 3 + 255) / 256, g.Hu), 256, 0, c->stream>>>(
+        c->staging, size_t(g.Wu) * 3, g.Hu, g.Wu, c->u, g, 0, 0);
+    c->launches++;
+  }
+  if (psf) {
+    const int KK2 = g.K * g.K;
+    CU(cudaMemcpyAsync(c->psf_hwc, psf, size_t(3) * KK2 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    k_psf_pack<<<(3 * KK2 + 255) / 256, 256, 0, c->stream>>>(c->psf_hwc, c->psf, KK2, 1);
+    CU(cudaMemcpyAsync(c->psf_caller, c->psf, size_t(3) * KK2 * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+    c->launches++;
+  }
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(c->stream));   // the host arrays may be pageable views: do not outlive the call
+  c->uploaded = true;
+  return RLTV_OK;
+}
+
+int rltv_download(rltv_ctx* c, float* u, size_t u_rs, float* psf_caller, float* psf_refined) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  const Geom& g = c->g;
+  if (u) {
+    if (u_rs < size_t(g.Wu) * 12) return fail(RLTV_ERR_ARG, "u row stride smaller than a packed row");
+    k_planar_to_hwc<<<dim3((g.Wu * 3 + 255) / 256 > 64 ? 64 : (g.Wu * 3 + 255) / 256, g.Hu), 256, 0, c->stream>>>(
+        c->u, g, 0, 0, g.Hu, g.Wu, c->staging, size_t(g.Wu) * 3);
+    c->launches++;
+    CU(cudaMemcpy2DAsync(u, u_rs, c->staging, size_t(g.Wu) * 12, size_t(g.Wu) * 12, g.Hu, cudaMemcpyDeviceToHost, c->stream));
+  }
+  const int KK2 = g.K * g.K;
+  float* dsts[2] = {psf_caller, psf_refined};
+  float* srcs[2] = {c->psf_caller, c->psf};
+  for (int i = 0; i < 2; ++i) {
+    if (!dsts[i]) continue;
+    k_psf_pack<<<(3 * KK2 + 255) / 256, 256, 0, c->stream>>>(c->psf_hwc, srcs[i], KK2, 0);
+    c->launches++;
+    CU(cudaMemcpyAsync(dsts[i], c->psf_hwc, size_t(3) * KK2 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(c->stream));
+  return RLTV_OK;
+}
+
+int rltv_begin(rltv_ctx* c, const rltv_params_t* p) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  if (!p) return fail(RLTV_ERR_ARG, "null params");
+  if (!c->uploaded) return fail(RLTV_ERR_STATE, "rltv_upload must precede rltv_begin/rltv_solve");
+  if (p->iterations < 0) return fail(RLTV_ERR_ARG, "negative iteration count");
+  c->params = *p;
+  rc = setup_whiteness(c, p->top, p->bottom, p->left, p->right);
+  if (rc) return rc;
+  CU(cudaMemsetAsync(c->st, 0, sizeof(State), c->stream));
+  c->outer_enqueued = 0;
+  c->launches = 0;
+  for (int f = 0; f < F_COUNT; ++f) { c->prof_ms[f] = 0.f; c->prof_n[f] = 0; c->prof_used[f] = 0; }
+  c->begun = true;
+  CU(cudaEventRecord(c->ev0, c->stream));
+  return RLTV_OK;
+}
+
+int rltv_enqueue_outer(rltv_ctx* c, int32_t n_outer) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  if (!c->begun) return fail(RLTV_ERR_STATE, "rltv_begin must precede rltv_enqueue_outer");
+  for (int i = 0; i < n_outer; ++i) {
+    if ((rc = enqueue_outer(c)) != RLTV_OK) return rc;
+    c->outer_enqueued++;
+  }
+  return RLTV_OK;
+}
+
+int rltv_finish(rltv_ctx* c, rltv_stats_t* stats) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  CU(cudaEventRecord(c->ev1, c->stream));
+  CU(cudaMemcpyAsync(c->h_st, c->st, sizeof(State), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+  if (c->prof) prof_collect(c);
+  fill_stats(c, stats, ms);
+  return RLTV_OK;
+}
+
+int rltv_solve(rltv_ctx* c, const rltv_params_t* p, rltv_stats_t* stats) {
+  int rc = rltv_begin(c, p);
+  if (rc) return rc;
+  // Host runs at most two outer iterations ahead of the device-side stop flag.
+  for (int it = 0; it < p->iterations; ++it) {
+    if (it >= 2) {
+      const int slot = (it - 2) & 3;
+      CU(cudaEventSynchronize(c->poll_ev[slot]));
+      if (c->h_poll[2 * slot]) break;
+    }
+    if ((rc = enqueue_outer(c)) != RLTV_OK) return rc;
+    c->outer_enqueued++;
+    const int slot = it & 3;
+    CU(cudaMemcpyAsync(c->h_poll + 2 * slot, c->st, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaEventRecord(c->poll_ev[slot], c->stream));
+  }
+  return rltv_finish(c, stats);
+}
+
+int rltv_profile_enable(rltv_ctx* c, int32_t on) {
+  if (!c) return fail(RLTV_ERR_ARG, "null context");
+  c->prof = on != 0;
+  return RLTV_OK;
+}
+
+int rltv_profile_get(rltv_ctx* c, const char* family, float* total_ms, int32_t* launches) {
+  if (!c || !family) return fail(RLTV_ERR_ARG, "null argument");
+  for (int f = 0; f < F_COUNT; ++f)
+    if (std::strcmp(family, kFamilyNames[f]) == 0) {
+      if (total_ms) *total_ms = c->prof_ms[f];
+      if (launches) *launches = c->prof_n[f];
+      return RLTV_OK;
+    }
+  return fail(RLTV_ERR_ARG, "unknown kernel family");
+}
+
+// ---- stage-level entry points ------------------------------------------------------------------------
+int rltv_stage_residual(rltv_ctx* c, float* err_out) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  if (!c->uploaded) return fail(RLTV_ERR_STATE, "upload first");
+  const Geom& g = c->g;
+  CU(cudaMemsetAsync(c->st, 0, sizeof(State), c->stream));
+  if ((rc = launch_conv_fwd(c)) != RLTV_OK) return rc;
+  if (err_out) {
+    k_planar_to_hwc<<<dim3(8, g.M), 256, 0, c->stream>>>(c->err, g, g.P, g.P, g.M, g.N, c->staging, size_t(g.N) * 3);
+    CU(cudaMemcpyAsync(err_out, c->staging, size_t(g.M) * g.N * 12, cudaMemcpyDeviceToHost, c->stream));
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  return RLTV_OK;
+}
+
+int rltv_stage_adjoint(rltv_ctx* c, float* g_out) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  if (!c->uploaded) return fail(RLTV_ERR_STATE, "upload first");
+  const Geom& g = c->g;
+  CU(cudaMemcpyAsync(c->ut, c->u, 3 * g.plane * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+  if ((rc = launch_conv_adj(c, 1.0f)) != RLTV_OK) return rc;
+  if (g_out) {
+    k_planar_to_hwc<<<dim3(8, g.Hu), 256, 0, c->stream>>>(c->gbuf, g, 0, 0, g.Hu, g.Wu, c->staging, size_t(g.Wu) * 3);
+    CU(cudaMemcpyAsync(g_out, c->staging, size_t(g.Hu) * g.Wu * 12, cudaMemcpyDeviceToHost, c->stream));
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  return RLTV_OK;
+}
+
+int rltv_stage_gradk(rltv_ctx* c, float* gk_out) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  if (!c->uploaded) return fail(RLTV_ERR_STATE, "upload first");
+  const int K = c->g.K, KK2 = K * K;
+  if ((rc = launch_gradk(c)) != RLTV_OK) return rc;
+  std::vector<double> p2(size_t(3) * NCH * KK2);
+  CU(cudaMemcpyAsync(p2.data(), c->gk_partial2, p2.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  // final fixed-order sum + the K-1-q index flip, exactly as k_psf_update does it
+  for (int ch = 0; ch < 3; ++ch)
+    for (int q = 0; q < KK2; ++q) {
+      const int qy = q / K, qx = q % K;
+      const int o = (K - 1 - qy) * K + (K - 1 - qx);
+      double s = 0.0;
+      for (int k = 0; k < NCH; ++k) s += p2[(size_t(ch) * NCH + k) * KK2 + o];
+      gk_out[q * 3 + ch] = float(s);
+    }
+  return RLTV_OK;
+}
+
+int rltv_stage_whiteness(rltv_ctx* c, int32_t top, int32_t bottom, int32_t left, int32_t right, float* M_r) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  if (!c->uploaded) return fail(RLTV_ERR_STATE, "upload first");
+  if ((rc = setup_whiteness(c, top, bottom, left, right)) != RLTV_OK) return rc;
+  if ((rc = launch_whiteness(c, 0)) != RLTV_OK) return rc;
+  float v = 0.f;
+  CU(cudaMemcpyAsync(&v, c->mr_out, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  if (M_r) *M_r = v;
+  return RLTV_OK;
+}
+
+// ---- one-shot drop-ins -------------------------------------------------------------------------------
+int rltv_richardson_lucy_mm(const float* image, size_t image_rs, float* u, size_t u_rs, float* psf, int32_t M,
+                            int32_t N, int32_t MK, const rltv_params_t* params, rltv_stats_t* stats,
+                            float* psf_refined, int32_t device) {
+  if (!image || !u || !psf || !params) return fail(RLTV_ERR_ARG, "null argument");
+  rltv_ctx* c = nullptr;
+  int rc = rltv_create(&c, device, M, N, MK, nullptr);
+  if (rc) return rc;
+  rc = rltv_upload(c, image, image_rs, u, u_rs, psf);
+  if (!rc) rc = rltv_solve(c, params, stats);
+  if (!rc) rc = rltv_download(c, u, u_rs, psf, psf_refined);
+  std::string keep = g_err;
+  rltv_destroy(c);
+  g_err = keep;
+  return rc;
+}
+
+int rltv_normalize_kernel(float* kern, int32_t MK, int32_t device) {
+  if (!kern || MK < 1) return fail(RLTV_ERR_ARG, "bad kernel");
+  if (rltv_device_count() <= 0) return fail(RLTV_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+  CU(cudaSetDevice(device));
+  const int KK2 = MK * MK;
+  float *d_hwc = nullptr, *d_pl = nullptr;
+  CU(cudaMalloc(&d_hwc, size_t(3) * KK2 * sizeof(float)));
+  CU(cudaMalloc(&d_pl, size_t(3) * KK2 * sizeof(float)));
+  CU(cudaMemcpy(d_hwc, kern, size_t(3) * KK2 * sizeof(float), cudaMemcpyHostToDevice));
+  k_psf_pack<<<(3 * KK2 + 255) / 256, 256>>>(d_hwc, d_pl, KK2, 1);
+  k_normalize_kernel<<<1, 128>>>(d_pl, KK2);
+  k_psf_pack<<<(3 * KK2 + 255) / 256, 256>>>(d_hwc, d_pl, KK2, 0);
+  cudaError_t e = cudaMemcpy(kern, d_hwc, size_t(3) * KK2 * sizeof(float), cudaMemcpyDeviceToHost);
+  cudaFree(d_hwc);
+  cudaFree(d_pl);
+  if (e != cudaSuccess) return fail(RLTV_ERR_CUDA, cudaGetErrorString(e));
+  return RLTV_OK;
+}
+
+}  // extern "C"

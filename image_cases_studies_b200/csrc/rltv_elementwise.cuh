@@ -1,0 +1,186 @@
+// Elementwise / reduction kernels of one inner step: the fused gradient-step + depth-of-field blend,
+// the PSF step + clip-and-normalise projection, and layout conversion at the host boundary.
+#pragma once
+#include "rltv_common.cuh"
+
+namespace rltv {
+
+// ------------------------------------------------------------------------------------------------
+// K3: u -= dt_c * (lambda*g + (u-ut)/2) on the whole padded domain (pyx:519-531), then on the interior
+//     DoF = ((g - I)/(g + I))^2 [/lambda if non-blind] ; u = (1-DoF)*u + DoF*I          (pyx:499-502, :552)
+// One float4 per thread per plane row; all five operands share the same (aligned) geometry.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_update(Geom g, State* __restrict__ st, float* __restrict__ u, const float* __restrict__ ut,
+         const float* __restrict__ gbuf, const float* __restrict__ img, float step, float lambd, int blind) {
+  if (st->stop) return;
+  const int c = blockIdx.z;
+  const int Y = blockIdx.y;
+  const int X = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+  // dt = step_factor * (amax(u_c) + 0) / (amax|gradu_c| + 1e-15), float32 like the reference (pyx:524)
+  const float dt = step * ord2f(st->max_u[c]) / (ord2f(st->max_G[c]) + 1e-15f);
+  if (X == 0 && Y == 0) st->dt[c] = dt;
+  if (X >= g.Wu) return;
+  const size_t off = size_t(c) * g.plane + size_t(Y) * g.pitch + X;
+  const float4 uv = *reinterpret_cast<const float4*>(u + off);
+  const float4 tv = *reinterpret_cast<const float4*>(ut + off);
+  const float4 gv = *reinterpret_cast<const float4*>(gbuf + off);
+  const float4 iv = *reinterpret_cast<const float4*>(img + off);
+  const float uu[4] = {uv.x, uv.y, uv.z, uv.w}, tt[4] = {tv.x, tv.y, tv.z, tv.w};
+  const float gg[4] = {gv.x, gv.y, gv.z, gv.w}, ii[4] = {iv.x, iv.y, iv.z, iv.w};
+  const bool rowin = (Y >= g.P) && (Y < g.P + g.M);
+  float o[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float G = fmaf(lambd, gg[i], 0.5f * (uu[i] - tt[i]));
+    float un = fmaf(-dt, G, uu[i]);
+    if (rowin && (X + i) >= g.P && (X + i) < g.P + g.N) {
+      const float d = (gg[i] - ii[i]) / (gg[i] + ii[i]);
+      float dof = d * d;
+      if (!blind) dof = dof / lambd;
+      un = (1.f - dof) * un + dof * ii[i];
+    }
+    o[i] = ((X + i) < g.Wu) ? un : uu[i];
+  }
+  *reinterpret_cast<float4*>(u + off) = make_float4(o[0], o[1], o[2], o[3]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: PSF step (pyx:574-589).  One block.  psf / psf_caller layout: planar [3][K*K].
+//   gk[q] = gk'[K-1-q] (sum of the NCH double partials); dtpsf = step/K * amax(psf) / (amax|gk| + 1e-15);
+//   psf -= dtpsf * gk ; (correlation: every channel = channel mean) ; clip < 0 ; divide by channel sum.
+// `psf_caller` reproduces what the CALLER's array holds in the reference: it tracks psf, except that with
+// `correlation` it freezes after the first un-normalised step (pyx:581 writes in place, pyx:585 rebinds).
+// ------------------------------------------------------------------------------------------------
+template <int NCH>
+__global__ void __launch_bounds__(256)
+k_psf_update(State* __restrict__ st, const double* __restrict__ partial2, int K, float step, int correlation,
+             float* __restrict__ psf, float* __restrict__ psf_caller) {
+  if (st->stop) return;
+  extern __shared__ float sm[];
+  const int KK2 = K * K;
+  float* gk = sm;              // [3][KK2]
+  float* pk = sm + 3 * KK2;    // [3][KK2]
+  __shared__ float red[8];
+  __shared__ float s_dtp;
+  __shared__ double s_sum[3];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float mg = 0.f, mp = -INFINITY;
+  for (int i = tid; i < 3 * KK2; i += blockDim.x) {
+    const int c = i / KK2, q = i - c * KK2;
+    const int qy = q / K, qx = q - qy * K;
+    const int o = (K - 1 - qy) * K + (K - 1 - qx);
+    double s = 0.0;
+    for (int ch = 0; ch < NCH; ++ch) s += partial2[(size_t(c) * NCH + ch) * KK2 + o];
+    const float v = float(s);
+    gk[i] = v;
+    const float p = psf[i];
+    pk[i] = p;
+    mg = fmaxf(mg, fabsf(v));
+    mp = fmaxf(mp, p);
+  }
+  mg = warp_max(mg);
+  if (lane == 0) red[warp] = mg;
+  __syncthreads();
+  if (tid == 0) { float m = 0.f; for (int w = 0; w < 8; ++w) m = fmaxf(m, red[w]); s_dtp = m; }
+  __syncthreads();
+  const float amax_gk = s_dtp;
+  __syncthreads();
+  mp = warp_max(mp);
+  if (lane == 0) red[warp] = mp;
+  __syncthreads();
+  if (tid == 0) {
+    float m = -INFINITY; for (int w = 0; w < 8; ++w) m = fmaxf(m, red[w]);
+    const float dtp = (step / float(K)) * m / (amax_gk + 1e-15f);      // pyx:574
+    s_dtp = dtp;
+    st->dtpsf = dtp;
+  }
+  __syncthreads();
+  const float dtp = s_dtp;
+  const bool first = (st->blind_steps == 0);
+  for (int i = tid; i < 3 * KK2; i += blockDim.x) {
+    const float v = fmaf(-dtp, gk[i], pk[i]);                          // pyx:581
+    pk[i] = v;
+    if (correlation && first) psf_caller[i] = v;                       // the caller's array stops here (pyx:585)
+  }
+  __syncthreads();
+  if (correlation) {
+    for (int q = tid; q < KK2; q += blockDim.x) {
+      const float m = (pk[q] + pk[KK2 + q] + pk[2 * KK2 + q]) / 3.f;   // np.mean(psf, axis=2), pyx:585
+      pk[q] = m; pk[KK2 + q] = m; pk[2 * KK2 + q] = m;
+    }
+    __syncthreads();
+  }
+  // clip + per-channel sum (pyx:58-64); warp c sums channel c in a fixed order
+  if (warp < 3) {
+    double s = 0.0;
+    for (int q = lane; q < KK2; q += 32) {
+      float v = pk[warp * KK2 + q];
+      if (v < 0.f) v = 0.f;
+      pk[warp * KK2 + q] = v;
+      s += double(v);
+    }
+    s = warp_sum(s);
+    if (lane == 0) s_sum[warp] = s;
+  }
+  __syncthreads();
+  for (int i = tid; i < 3 * KK2; i += blockDim.x) {
+    const float v = pk[i] / float(s_sum[i / KK2]);                     // pyx:67-70
+    psf[i] = v;
+    if (!correlation) psf_caller[i] = v;
+  }
+  if (tid == 0) st->blind_steps += 1;
+}
+
+// normalize_kernel (pyx:73-75): same clip + normalise on a planar [3][K*K] buffer, one block.
+__global__ void __launch_bounds__(128)
+k_normalize_kernel(float* __restrict__ kern, int KK2) {
+  __shared__ double s_sum[3];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp < 3) {
+    double s = 0.0;
+    for (int q = lane; q < KK2; q += 32) {
+      float v = kern[warp * KK2 + q];
+      if (v < 0.f) v = 0.f;
+      kern[warp * KK2 + q] = v;
+      s += double(v);
+    }
+    s = warp_sum(s);
+    if (lane == 0) s_sum[warp] = s;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * KK2; i += blockDim.x) kern[i] = kern[i] / float(s_sum[i / KK2]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host-boundary layout conversion: packed HWC rows <-> planar u-geometry planes.
+// src: rows x cols pixels, `src_pitch` floats per row (packed RGB); dst planes at offset (oy, ox).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_hwc_to_planar(const float* __restrict__ src, size_t src_pitch, int rows, int cols,
+                                float* __restrict__ dst, Geom g, int oy, int ox) {
+  const int y = blockIdx.y;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < cols * 3; e += gridDim.x * blockDim.x) {
+    const int x = e / 3, c = e - 3 * x;
+    dst[size_t(c) * g.plane + size_t(y + oy) * g.pitch + (x + ox)] = src[size_t(y) * src_pitch + e];
+  }
+}
+
+__global__ void k_planar_to_hwc(const float* __restrict__ src, Geom g, int oy, int ox, int rows, int cols,
+                                float* __restrict__ dst, size_t dst_pitch) {
+  const int y = blockIdx.y;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < cols * 3; e += gridDim.x * blockDim.x) {
+    const int x = e / 3, c = e - 3 * x;
+    dst[size_t(y) * dst_pitch + e] = src[size_t(c) * g.plane + size_t(y + oy) * g.pitch + (x + ox)];
+  }
+}
+
+// [K][K][3] packed <-> [3][K*K] planar (PSF)
+__global__ void k_psf_pack(float* __restrict__ hwc, float* __restrict__ planar, int KK2, int to_planar) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 3 * KK2; i += gridDim.x * blockDim.x) {
+    const int q = i / 3, c = i - 3 * q;
+    if (to_planar) planar[c * KK2 + q] = hwc[i];
+    else hwc[i] = planar[c * KK2 + q];
+  }
+}
+
+}  // namespace rltv

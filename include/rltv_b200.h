@@ -1,0 +1,127 @@
+/*
+ * rltv_b200.h -- C ABI of the B200-native Richardson-Lucy / MM deconvolution hot path.
+ *
+ * Drop-in boundary for the solver of aurelienpierre/Image-Cases-Studies:
+ *   lib/deconvolution.pyx:341-342  cpdef richardson_lucy_MM(image, u, psf, top, bottom, left, right, tau,
+ *                                        M, N, C, MK, iterations, step_factor, lambd, blind, correlation, ...)
+ *   lib/deconvolution.pyx:73-75    cpdef normalize_kernel(kern, MK)
+ * The reference has no FFI of its own (it is a Cython module called from Python,
+ * deconvolve.py:21,:250,:277,:291,:304); the entry points below are what a ctypes/cffi binding of that
+ * module binds instead.  Plain pointers, sizes and byte strides only.
+ *
+ * Conventions
+ *   - all pixel data is float32; host arrays are HWC with packed RGB pixels (channel stride 4 bytes,
+ *     pixel stride 12 bytes) and an arbitrary ROW stride in bytes (the reference's callers pass row-sliced
+ *     views, deconvolve.py:277-286);
+ *   - `u` has shape (M + MK - 1, N + MK - 1, 3): the estimate with its pad = MK/2 ring (pyx:376);
+ *   - `psf` has shape (MK, MK, 3), packed;
+ *   - every function returns 0 on success or a negative rltv_status; rltv_last_error() gives the text.
+ *     No exceptions, no torch types cross this boundary.  There is no CPU fallback: without a CUDA device
+ *     every compute entry point returns RLTV_ERR_CUDA.
+ */
+#ifndef RLTV_B200_H
+#define RLTV_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RLTV_ABI_VERSION 1
+#define RLTV_INNER_ITER 5       /* pyx:375 */
+#define RLTV_MAX_MK 63          /* direct stencils are instantiated for odd MK in [3, 63] */
+#define RLTV_MAX_HISTORY 4096   /* outer iterations whose M_r is kept in rltv_stats_t.M_r_history */
+
+typedef enum {
+  RLTV_OK = 0,
+  RLTV_ERR_ARG = -1,      /* bad shape / parameter: the Python wrapper raises ValueError */
+  RLTV_ERR_CUDA = -2,     /* CUDA runtime error (including "no device") */
+  RLTV_ERR_ALLOC = -3,
+  RLTV_ERR_STATE = -4     /* call order (e.g. solve before upload) */
+} rltv_status;
+
+/* Solver parameters: the scalar arguments of richardson_lucy_MM (pyx:341-342). */
+typedef struct {
+  int32_t top, bottom, left, right; /* whiteness window in image coordinates (pyx:627) */
+  float tau;                        /* non-blind stop threshold (pyx:652) */
+  int32_t iterations;               /* max OUTER iterations; each runs RLTV_INNER_ITER inner steps */
+  float step_factor;                /* pyx:524, :574 */
+  float lambd;                      /* pyx:502, :519 */
+  int32_t blind;                    /* pyx:555 */
+  int32_t correlation;              /* pyx:584-585 (channel-mean PSF) */
+} rltv_params_t;
+
+typedef struct {
+  int32_t iterations_executed;      /* outer iterations run (pyx:656) */
+  int32_t stopped;                  /* stop_flag (pyx:647,:653) */
+  float M_r, M_r_prev;              /* whiteness statistic of the last two outer iterations (pyx:638) */
+  float dt[3];                      /* last image step sizes (pyx:524) */
+  float dtpsf;                      /* last PSF step size (pyx:574) */
+  float solve_ms;                   /* device time of the solve (CUDA events on the solver stream) */
+  int32_t kernel_launches;          /* kernels launched by this solve */
+  int32_t n_history;
+  float M_r_history[RLTV_MAX_HISTORY];
+} rltv_stats_t;
+
+typedef struct rltv_ctx rltv_ctx;
+
+int rltv_abi_version(void);
+const char* rltv_last_error(void);
+int rltv_device_count(void);      /* number of CUDA devices, 0 if none, <0 on error */
+
+/* ---- one-shot host entry points (exact drop-ins) -------------------------------------------------- */
+
+/* richardson_lucy_MM (pyx:341-675).  `u` and `psf` are updated IN PLACE (pyx:531,:552,:581); the caller's
+ * result is the view u[pad:pad+M, pad:pad+N] (pyx:675).  With `correlation` set, `psf` receives what the
+ * reference leaves in the caller's array: one un-normalised step (pyx:581), because pyx:585 rebinds the
+ * local name; the solver's own refined PSF is returned through `psf_refined` when it is not NULL. */
+int rltv_richardson_lucy_mm(const float* image, size_t image_row_stride_bytes,
+                            float* u, size_t u_row_stride_bytes,
+                            float* psf,
+                            int32_t M, int32_t N, int32_t MK,
+                            const rltv_params_t* params, rltv_stats_t* stats,
+                            float* psf_refined, int32_t device);
+
+/* normalize_kernel (pyx:73-75 -> :47-70): clip negatives, divide each channel by its sum; in place. */
+int rltv_normalize_kernel(float* kern, int32_t MK, int32_t device);
+
+/* ---- persistent context (device-resident state; what bench.py times and the multi-GPU driver uses) -- */
+
+/* `stream` is a cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream) or NULL for a private one.
+ * The context owns planar device copies of image/u/ut/g/err for an (M,N,MK) problem.
+ * Row-band sharding: the context may hold only rows [row0, row0+rows) of a frame of `M_total` rows. */
+int rltv_create(rltv_ctx** ctx, int32_t device, int32_t M, int32_t N, int32_t MK, void* stream);
+int rltv_destroy(rltv_ctx* ctx);
+int rltv_upload(rltv_ctx* ctx, const float* image, size_t image_row_stride_bytes,
+                const float* u, size_t u_row_stride_bytes, const float* psf);
+int rltv_download(rltv_ctx* ctx, float* u, size_t u_row_stride_bytes, float* psf_caller, float* psf_refined);
+/* Runs up to params->iterations outer iterations on the device-resident state (resets the iteration
+ * counter and the stop flag first).  Synchronises the stream before returning. */
+int rltv_solve(rltv_ctx* ctx, const rltv_params_t* params, rltv_stats_t* stats);
+/* Enqueue `n_outer` outer iterations without synchronising and without touching the counters
+ * (used by bench.py to time steady-state steps with CUDA events on the same stream). */
+int rltv_begin(rltv_ctx* ctx, const rltv_params_t* params);
+int rltv_enqueue_outer(rltv_ctx* ctx, int32_t n_outer);
+int rltv_finish(rltv_ctx* ctx, rltv_stats_t* stats);
+void* rltv_stream(rltv_ctx* ctx);
+/* Time (ms, CUDA events on the context's stream) and launch count of each kernel family since the last
+ * rltv_begin, for bench.py's roofline.  names: "conv_fwd","conv_adj","update","gradk","psf","stats","copy". */
+int rltv_profile_enable(rltv_ctx* ctx, int32_t on);
+int rltv_profile_get(rltv_ctx* ctx, const char* family, float* total_ms, int32_t* launches);
+
+/* ---- stage-level entry points (parity tests drive each kernel against the oracle) ------------------ */
+/* out[M][N][3] = valid-conv(u, psf) - image   (pyx:477-488) */
+int rltv_stage_residual(rltv_ctx* ctx, float* err_out /* packed HWC (M,N,3) */);
+/* g = full-conv(err, rot180(psf)) on the u domain (pyx:490-491), using the residual currently on device */
+int rltv_stage_adjoint(rltv_ctx* ctx, float* g_out /* packed HWC (M+MK-1, N+MK-1, 3) */);
+/* gk = valid-conv(rot180(u), err) (pyx:567-571) using the residual currently on device */
+int rltv_stage_gradk(rltv_ctx* ctx, float* gk_out /* packed (MK,MK,3) */);
+/* whiteness statistic of the residual window (pyx:627-638) */
+int rltv_stage_whiteness(rltv_ctx* ctx, int32_t top, int32_t bottom, int32_t left, int32_t right, float* M_r);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RLTV_B200_H */

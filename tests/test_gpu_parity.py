@@ -1,0 +1,198 @@
+"""GPU parity tests (run on the B200 box with -m gpu): the CUDA path, called through the C ABI / the
+drop-in module, against (a) the committed golden vectors of the compiled reference, (b) the numpy oracle on
+seeded inputs, (c) oracle/_ref run live when it travelled, (d) size-independent properties at full size.
+
+Tolerances (BASELINE.json north_star): image rel-L2 <= 1e-4, PSF L1 <= 1e-4, equal outer-iteration counts.
+"""
+import numpy as np
+import pytest
+
+from helpers import TOL_IMAGE_REL_L2, TOL_PSF_L1, golden_names, load_golden, psf_l1, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dc():
+    import __graft_entry__ as g
+    g.build()
+    from image_cases_studies_b200.lib import deconvolution
+    return deconvolution
+
+
+def _run_dc(dc, g):
+    M, N = g["image"].shape[:2]
+    MK = g["psf0"].shape[0]
+    u = g["u0"].copy()
+    psf = g["psf0"].copy()
+    out = dc.richardson_lucy_MM(g["image"].copy(), u, psf, *g["window"], g["tau"], M, N, 3, MK, g["iterations"],
+                                g["step_factor"], g["lambd"], blind=g["blind"], correlation=g["correlation"])
+    return out, u, psf, dict(dc.last_stats)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_golden_vectors(dc, name):
+    g = load_golden(name)
+    out, u, psf, st = _run_dc(dc, g)
+    assert np.shares_memory(out, u)                      # the result is a view of the caller's u (pyx:675)
+    assert st["iterations"] == g["ref_iterations"]
+    assert rel_l2(out, g["ref_out"]) <= TOL_IMAGE_REL_L2
+    assert rel_l2(u, g["ref_u"]) <= TOL_IMAGE_REL_L2
+    assert psf_l1(psf, g["ref_psf"]) <= TOL_PSF_L1
+    # in blind mode the output moves away from the input by only ~3e-5 (DoF ~ 1), so also check the update itself
+    upd_ref = g["ref_out"].astype(np.float64) - g["image"]
+    upd = out.astype(np.float64) - g["image"]
+    assert np.linalg.norm(upd - upd_ref) <= 0.02 * np.linalg.norm(upd_ref) + 1e-6 * np.linalg.norm(g["image"])
+
+
+@pytest.mark.parametrize("K", [3, 5, 7, 9, 11, 13, 15, 17, 19, 25, 31])
+def test_stages_against_oracle(K):
+    """Forward residual, adjoint and PSF gradient, each kernel alone against the float64 definition."""
+    from image_cases_studies_b200.solver import Solver
+    from oracle import rl_mm_oracle as orc
+    rng = np.random.default_rng(K)
+    M, N = 70 + 3 * K, 150 + K            # not multiples of the tile sizes
+    u = rng.random((M + K - 1, N + K - 1, 3), dtype=np.float32)
+    image = rng.random((M, N, 3), dtype=np.float32)
+    psf = rng.random((K, K, 3), dtype=np.float32)
+    psf /= psf.sum(axis=(0, 1), keepdims=True)
+    s = Solver(M, N, K)
+    s.upload(image, u, psf)
+    err = s.stage_residual()
+    g = s.stage_adjoint()
+    gk = s.stage_gradk()
+    s.close()
+    for c in range(3):
+        e_ref = orc.conv2(u[..., c], psf[..., c], "valid") - image[..., c]
+        assert rel_l2(err[..., c], e_ref) < 2e-6
+        g_ref = orc.conv2(e_ref, orc.rot180(psf[..., c]), "full")
+        assert rel_l2(g[..., c], g_ref) < 3e-6
+        gk_ref = orc.conv2(orc.rot180(u[..., c]), e_ref, "valid")
+        assert rel_l2(gk[..., c], gk_ref) < 1e-5
+
+
+@pytest.mark.parametrize("win", [(4, 60, 4, 60), (3, 120, 10, 97), (0, 33, 5, 200)])
+def test_whiteness_statistic(win):
+    from image_cases_studies_b200.solver import Solver
+    from oracle import rl_mm_oracle as orc
+    rng = np.random.default_rng(5)
+    M, N, K = 140, 230, 5
+    u = rng.random((M + K - 1, N + K - 1, 3), dtype=np.float32)
+    image = rng.random((M, N, 3), dtype=np.float32)
+    psf = np.full((K, K, 3), 1.0 / (K * K), np.float32)
+    s = Solver(M, N, K)
+    s.upload(image, u, psf)
+    err = s.stage_residual()
+    m_gpu = s.stage_whiteness(win)
+    s.close()
+    top, bottom, left, right = win
+    m_ref = orc.whiteness(err[top:bottom, left:right].astype(np.float64), orc.whiteness_weights(bottom - top, right - left))
+    assert abs(m_gpu - m_ref) <= 2e-6 * abs(m_ref)
+
+
+@pytest.mark.parametrize("name,scale,iters", [("c1_nonblind_512_g5", 1.0, 10), ("c2_blind_2mp_k9", 0.25, 6),
+                                              ("c3_blind_24mp_k15", 0.06, 3), ("c5_nonblind_4k_kaiser7", 0.1, 3)])
+def test_workloads_against_oracle(dc, name, scale, iters):
+    from image_cases_studies_b200 import synthetic
+    from oracle import rl_mm_oracle as orc
+    c = synthetic.make_case(name, seed=7, scale=scale, iterations=iters)
+    M, N = c.shape
+    g = dict(image=c.image, u0=c.u0, psf0=c.psf0, window=c.window, tau=c.tau, iterations=c.iterations,
+             step_factor=c.step_factor, lambd=c.lambd, blind=c.blind, correlation=False)
+    out, u, psf, st = _run_dc(dc, g)
+    ref = orc.richardson_lucy_MM(c.image, c.u0, c.psf0, *c.window, c.tau, M, N, 3, c.MK, c.iterations,
+                                 c.step_factor, c.lambd, blind=c.blind)
+    assert st["iterations"] == ref.iterations
+    assert rel_l2(out, ref.out) <= TOL_IMAGE_REL_L2
+    assert psf_l1(psf, ref.psf) <= TOL_PSF_L1
+    assert np.allclose(st["M_r_history"], ref.M_r, rtol=2e-5)
+    for a, b in zip(st["dt"], ref.dt[-1]):
+        assert abs(a - b) <= 1e-4 * abs(b)
+
+
+def test_live_reference_when_present(dc):
+    from oracle import ref_loader
+    if ref_loader.so_path() is None:
+        pytest.skip("oracle/_ref did not travel")
+    from image_cases_studies_b200 import synthetic
+    for name, scale, iters in (("c2_blind_2mp_k9", 0.2, 5), ("c1_nonblind_512_g5", 0.75, 5)):
+        c = synthetic.make_case(name, seed=9, scale=scale, iterations=iters)
+        M, N = c.shape
+        out_r, u_r, psf_r, log = ref_loader.run(c.image, c.u0, c.psf0, c.window, c.tau, c.iterations, c.step_factor,
+                                                c.lambd, c.blind)
+        g = dict(image=c.image, u0=c.u0, psf0=c.psf0, window=c.window, tau=c.tau, iterations=c.iterations,
+                 step_factor=c.step_factor, lambd=c.lambd, blind=c.blind, correlation=False)
+        out, u, psf, st = _run_dc(dc, g)
+        assert st["iterations"] == ref_loader.executed_iterations(log)
+        assert rel_l2(out, out_r) <= TOL_IMAGE_REL_L2 and psf_l1(psf, psf_r) <= TOL_PSF_L1
+
+
+def test_strided_views_and_inplace_contract(dc):
+    """The reference's driver passes row/column-sliced views of larger frames (deconvolve.py:277-286)."""
+    from image_cases_studies_b200 import synthetic
+    c = synthetic.make_case("c2_blind_2mp_k9", seed=4, scale=0.08, iterations=2)
+    M, N = c.shape
+    p = c.MK // 2
+    big_img = np.zeros((M + 10, N + 14, 3), np.float32)
+    big_u = np.zeros((M + 2 * p + 6, N + 2 * p + 8, 3), np.float32)
+    img_v = big_img[3:3 + M, 5:5 + N]
+    u_v = big_u[2:2 + M + 2 * p, 4:4 + N + 2 * p]
+    img_v[...] = c.image
+    u_v[...] = c.u0
+    psf_a, psf_b = c.psf0.copy(), c.psf0.copy()
+    out_v = dc.richardson_lucy_MM(img_v, u_v, psf_a, *c.window, c.tau, M, N, 3, c.MK, 2, c.step_factor, c.lambd, blind=True)
+    u_c = c.u0.copy()
+    out_c = dc.richardson_lucy_MM(c.image, u_c, psf_b, *c.window, c.tau, M, N, 3, c.MK, 2, c.step_factor, c.lambd, blind=True)
+    assert np.shares_memory(out_v, big_u)
+    assert np.array_equal(out_v, out_c) and np.array_equal(psf_a, psf_b)      # bit-deterministic
+    assert np.array_equal(big_u[2:2 + M + 2 * p, 4:4 + N + 2 * p], u_c)
+    assert not big_u[:2].any() and not big_u[:, :4].any()                       # nothing outside the view was touched
+
+
+def test_normalize_kernel_golden(dc):
+    from helpers import GOLDEN
+    z = np.load(GOLDEN / "normalize_kernel_k7.npz")
+    k = z["kern"].copy()
+    assert dc.normalize_kernel(k, 7) is None
+    assert np.abs(k - z["ref"]).max() < 1e-6
+
+
+def test_nonblind_leaves_psf_untouched_and_zero_iterations(dc):
+    from image_cases_studies_b200 import synthetic
+    c = synthetic.make_case("c1_nonblind_512_g5", seed=2, scale=0.2, iterations=0)
+    M, N = c.shape
+    u, psf = c.u0.copy(), c.psf0.copy()
+    out = dc.richardson_lucy_MM(c.image, u, psf, *c.window, c.tau, M, N, 3, c.MK, 0, c.step_factor, c.lambd, blind=False)
+    assert np.array_equal(u, c.u0) and np.array_equal(psf, c.psf0) and dc.last_stats["iterations"] == 0
+    assert out.shape == (M, N, 3)
+
+
+def test_full_size_properties(dc):
+    """At BASELINE's 24 MP / 15x15 size the oracle is too slow; check size-independent properties instead:
+    PSF stays on the simplex, u ring/interior finite, determinism, and adjointness <Ku, e> == <u, K^T e>."""
+    from image_cases_studies_b200.solver import Solver
+    rng = np.random.default_rng(0)
+    M, N, K = 4000, 6000, 15
+    u = (0.1 + 0.8 * rng.random((M + K - 1, N + K - 1, 3), dtype=np.float32))
+    image = (0.1 + 0.8 * rng.random((M, N, 3), dtype=np.float32))
+    from image_cases_studies_b200.lib import utils
+    psf = utils.stack3(utils.gaussian_kernel(K, 3.0))
+    s = Solver(M, N, K)
+    s.upload(image, u, psf)
+    err = s.stage_residual()                       # err = K u - image
+    g = s.stage_adjoint()                          # g = K^T err
+    lhs = float(np.sum((err.astype(np.float64) + image) * err))        # <K u, err>
+    rhs = float(np.sum(u.astype(np.float64) * g))                      # <u, K^T err>
+    assert abs(lhs - rhs) <= 1e-5 * abs(lhs)
+    params = Solver.make_params((8, 247, 8, 247), 0.0, 1, 1e-3, 1e4, True)
+    st = s.solve(params)
+    u1, p1 = np.empty_like(u), np.empty_like(psf)
+    s.download(u1, p1)
+    assert st["iterations"] == 1 and np.isfinite(u1).all()
+    assert np.allclose(p1.sum(axis=(0, 1)), 1.0, atol=1e-5) and p1.min() >= 0
+    s.upload(image, u, psf)
+    s.solve(params)
+    u2, p2 = np.empty_like(u), np.empty_like(psf)
+    s.download(u2, p2)
+    s.close()
+    assert np.array_equal(u1, u2) and np.array_equal(p1, p2)
