@@ -5,6 +5,7 @@
 // Nothing is read back between kernels: step sizes, the PSF, the statistic and the stop flag live in a
 // device-resident State; once the flag is set every later kernel returns at its first instruction, so the
 // host may run ahead (it polls the flag two outer iterations behind, without draining the stream).
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -57,7 +58,10 @@ struct rltv_ctx {
   int* h_poll = nullptr;        // pinned ring: {stop, it} per slot
   cudaEvent_t poll_ev[4]{};
   float* gk_partial = nullptr;
-  int gk_ntiles = 0;
+  int gk_nparts = 0;            // CTAs of the persistent k_gradk grid (one partial each)
+  int num_sms = 148;
+  // TMA descriptors (rank-3 tensors x: Wu, y: Hu, c: 3 over the planar arrays; boxes per kernel)
+  CUtensorMap tm_u_conv{}, tm_err_conv{}, tm_img_epi{}, tm_u_epi{}, tm_ut_epi{}, tm_u_gk{}, tm_err_gk{};
   double* gk_partial2 = nullptr;
   float* gk_out = nullptr;
   // whiteness
@@ -121,61 +125,98 @@ void prof_collect(rltv_ctx* c) {
 #define RLTV_FOR_EACH_K(M) \
   M(3) M(5) M(7) M(9) M(11) M(13) M(15) M(17) M(19) M(21) M(23) M(25) M(27) M(29) M(31)
 
-template <int K>
-int launch_conv_fwd_t(rltv_ctx* c) {
-  using C = ConvCfg<K>;
-  static bool attr = false;
-  if (!attr) {
-    CU(cudaFuncSetAttribute(k_conv_fwd<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(C::SMEM_BYTES)));
-    attr = true;
+// ---- TMA descriptors ---------------------------------------------------------------------------------
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_tmapEncodeTiled tmap_encoder() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_tmapEncodeTiled>(p);
   }
-  dim3 grid((c->g.pitch + C::TW - 1) / C::TW, (c->g.Hu + C::TH - 1) / C::TH, 3);
-  ProfScope p(c, F_CONV_FWD);
-  k_conv_fwd<K><<<grid, C::THREADS, C::SMEM_BYTES, c->stream>>>(c->g, c->st, c->u, c->img, c->psf, c->err);
+  return fn;
+}
+
+// rank-3 view (x: Wu, y: Hu, c: 3) of one planar frame array, box = bw x bh x 1, zero fill out of bounds
+int make_tmap(CUtensorMap* tm, float* base, const Geom& g, int bw, int bh) {
+  PFN_tmapEncodeTiled enc = tmap_encoder();
+  if (!enc) return fail(RLTV_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[3] = {cuuint64_t(g.Wu), cuuint64_t(g.Hu), 3};
+  cuuint64_t strides[2] = {cuuint64_t(g.pitch) * 4, cuuint64_t(g.plane) * 4};
+  cuuint32_t box[3] = {cuuint32_t(bw), cuuint32_t(bh), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(RLTV_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string(int(r)));
   return RLTV_OK;
 }
 
 template <int K>
-int launch_conv_adj_t(rltv_ctx* c, float lambd) {
+int make_maps_t(rltv_ctx* c) {
   using C = ConvCfg<K>;
-  static bool attr = false;
-  if (!attr) {
-    CU(cudaFuncSetAttribute(k_conv_adj<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(C::SMEM_BYTES)));
-    attr = true;
-  }
-  dim3 grid((c->g.pitch + C::TW - 1) / C::TW, (c->g.Hu + C::TH - 1) / C::TH, 3);
-  ProfScope p(c, F_CONV_ADJ);
-  k_conv_adj<K><<<grid, C::THREADS, C::SMEM_BYTES, c->stream>>>(c->g, c->st, c->err, c->psf, c->u, c->ut, lambd, c->gbuf);
+  using G = GradkCfg<K>;
+  int rc;
+  if ((rc = make_tmap(&c->tm_u_conv, c->u, c->g, C::SP, C::SROWS))) return rc;
+  if ((rc = make_tmap(&c->tm_err_conv, c->err, c->g, C::SP, C::SROWS))) return rc;
+  if ((rc = make_tmap(&c->tm_img_epi, c->img, c->g, C::TW, C::TH))) return rc;
+  if ((rc = make_tmap(&c->tm_u_epi, c->u, c->g, C::TW, C::TH))) return rc;
+  if ((rc = make_tmap(&c->tm_ut_epi, c->ut, c->g, C::TW, C::TH))) return rc;
+  if ((rc = make_tmap(&c->tm_u_gk, c->u, c->g, G::SP, G::SROWS))) return rc;
+  if ((rc = make_tmap(&c->tm_err_gk, c->err, c->g, G::TW, G::TH))) return rc;
+  return RLTV_OK;
+}
+
+template <int K, bool ADJ>
+int launch_conv_t(rltv_ctx* c, float lambd) {
+  using C = ConvCfg<K>;
+  constexpr int SMEM = C::smem_bytes(ADJ);
+  CU(cudaFuncSetAttribute(k_conv<K, ADJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+  const int ntx = (c->g.pitch + C::TW - 1) / C::TW, nty = (c->g.Hu + C::TH - 1) / C::TH;
+  int grid = 2 * c->num_sms;
+  if (grid > 3 * ntx * nty) grid = 3 * ntx * nty;
+  ProfScope p(c, ADJ ? F_CONV_ADJ : F_CONV_FWD);
+  if (ADJ)
+    k_conv<K, true><<<grid, C::THREADS, SMEM, c->stream>>>(c->tm_err_conv, c->tm_u_epi, c->tm_ut_epi, c->g, c->st, c->psf,
+                                                          lambd, c->gbuf, ntx, nty);
+  else
+    k_conv<K, false><<<grid, C::THREADS, SMEM, c->stream>>>(c->tm_u_conv, c->tm_img_epi, c->tm_img_epi, c->g, c->st, c->psf,
+                                                           lambd, c->err, ntx, nty);
   return RLTV_OK;
 }
 
 template <int K>
-void gradk_grid_t(const Geom& g, int* gx, int* gy) {
-  using C = GradkCfg<K>;
-  *gx = (g.Wu + C::TW - 1) / C::TW;
-  *gy = (g.Hu + C::TH - 1) / C::TH;
-}
+int launch_conv_fwd_t(rltv_ctx* c) { return launch_conv_t<K, false>(c, 0.f); }
+template <int K>
+int launch_conv_adj_t(rltv_ctx* c, float lambd) { return launch_conv_t<K, true>(c, lambd); }
 
 template <int K>
 int launch_gradk_t(rltv_ctx* c) {
   using C = GradkCfg<K>;
-  static bool attr = false;
-  if (!attr) {
-    CU(cudaFuncSetAttribute(k_gradk<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(C::SMEM_BYTES)));
-    attr = true;
-  }
-  int gx, gy;
-  gradk_grid_t<K>(c->g, &gx, &gy);
-  dim3 grid(gx, gy, 3 * C::NCHUNK);
+  CU(cudaFuncSetAttribute(k_gradk<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+  const int ntx = (c->g.Wu + C::TW - 1) / C::TW, nty = (c->g.Hu + C::TH - 1) / C::TH;
   {
     ProfScope p(c, F_GRADK);
-    k_gradk<K><<<grid, C::THREADS, C::SMEM_BYTES, c->stream>>>(c->g, c->st, c->err, c->u, c->gk_partial);
+    k_gradk<K><<<c->gk_nparts, C::THREADS, C::SMEM_BYTES, c->stream>>>(c->tm_u_gk, c->tm_err_gk, c->g, c->st, c->gk_partial, ntx, nty);
   }
   {
     ProfScope p(c, F_GRADK);
-    k_gradk_reduce<NCH><<<dim3(NCH, 3), 256, 0, c->stream>>>(c->st, c->gk_partial, gx * gy, K * K, c->gk_partial2);
+    k_gradk_reduce<NCH><<<dim3(NCH, 3), 256, 0, c->stream>>>(c->st, c->gk_partial, c->gk_nparts, K * K, c->gk_partial2);
   }
   return RLTV_OK;
+}
+
+int make_maps(rltv_ctx* c) {
+  switch (c->g.K) {
+#define M(K_) case K_: return make_maps_t<K_>(c);
+    RLTV_FOR_EACH_K(M)
+#undef M
+  }
+  return fail(RLTV_ERR_ARG, "unsupported MK");
 }
 
 int launch_conv_fwd(rltv_ctx* c) {
@@ -202,16 +243,6 @@ int launch_gradk(rltv_ctx* c) {
   }
   return fail(RLTV_ERR_ARG, "unsupported MK");
 }
-int gradk_ntiles(const Geom& g) {
-  int gx = 0, gy = 0;
-  switch (g.K) {
-#define M(K_) case K_: gradk_grid_t<K_>(g, &gx, &gy); break;
-    RLTV_FOR_EACH_K(M)
-#undef M
-  }
-  return gx * gy;
-}
-
 int launch_update(rltv_ctx* c) {
   dim3 grid((c->g.pitch / 4 + 255) / 256, c->g.Hu, 3);
   ProfScope p(c, F_UPDATE);
@@ -428,8 +459,17 @@ int rltv_create(rltv_ctx** out, int32_t device, int32_t M, int32_t N, int32_t MK
   for (auto& e : c->poll_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   CU(cudaEventCreate(&c->ev0));
   CU(cudaEventCreate(&c->ev1));
-  c->gk_ntiles = gradk_ntiles(g);
-  CU(cudaMalloc(&c->gk_partial, size_t(3) * c->gk_ntiles * MK * MK * sizeof(float)));
+  {
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    c->num_sms = prop.multiProcessorCount;
+  }
+  c->gk_nparts = c->num_sms;   // persistent k_gradk: one CTA per SM, one partial per CTA
+  CU(cudaMalloc(&c->gk_partial, size_t(3) * c->gk_nparts * MK * MK * sizeof(float)));
+  {
+    int rc = make_maps(c);
+    if (rc) { std::string keep = g_err; rltv_destroy(c); g_err = keep; return rc; }
+  }
   CU(cudaMalloc(&c->gk_partial2, size_t(3) * NCH * MK * MK * sizeof(double)));
   CU(cudaStreamSynchronize(c->stream));
   *out = c;

@@ -1,7 +1,11 @@
 // Direct K x K stencil kernels: forward blur + residual, adjoint + step statistics, PSF-gradient
-// correlation.  FP32 FMA-pipe kernels: register-blocked (each thread owns X=4 adjacent outputs on R rows
-// and slides a rolling window of R input rows through registers), inputs staged in shared memory with a
-// zero-filled halo, PSF taps broadcast from shared memory as float4.
+// correlation.  FP32 FMA-pipe kernels, sm_100a:
+//   * persistent CTAs walk a static tile schedule; the input tile (+ K-1 halo, zero-filled at the frame
+//     border by the TMA unit) is double-buffered in shared memory, the next tile's cp.async.bulk.tensor
+//     load overlapping the current tile's FMAs; epilogue operands (image / u, ut) are TMA-staged too;
+//   * register blocking: each thread owns X=4 adjacent outputs on R rows and slides a rolling window of R
+//     input rows through registers (one LDS.128 row per ky, R*4*K FFMA per ky) -- ~96 % of the inner-loop
+//     instructions are FFMA; PSF taps are broadcast from shared memory as float4.
 //
 // Reference arithmetic being replaced (all three run as FFTs inside scipy.signal.convolve there):
 //   forward  : synth = convolve(u, psf, "valid"); error = synth - image        lib/deconvolution.pyx:477-488
@@ -12,8 +16,11 @@
 // with w = rot180(psf) for the forward blur (true convolution) and w = psf for the adjoint.
 #pragma once
 #include "rltv_common.cuh"
+#include "rltv_tma.cuh"
 
 namespace rltv {
+
+constexpr int align128(int bytes) { return (bytes + 127) & ~127; }
 
 // ------------------------------------------------------------------------------------------------
 // Tile configuration of the two convolution kernels
@@ -24,30 +31,24 @@ struct ConvCfg {
   static constexpr int R = (K <= 17) ? 4 : 2;       // output rows per thread == depth of the rolling window
   static constexpr int WARPS = 8;
   static constexpr int THREADS = 32 * WARPS;
-  static constexpr int TW = 32 * X;                 // 128 output columns per block
-  static constexpr int TH = WARPS * R;              // 32 (or 16) output rows per block
+  static constexpr int TW = 32 * X;                 // 128 output columns per tile
+  static constexpr int TH = WARPS * R;              // 32 (or 16) output rows per tile
   static constexpr int P = K / 2;
-  static constexpr int NV = (K + X - 1 + 3) / 4;    // float4 loads per window row (window = X + K - 1 floats)
-  static constexpr int SP = TW - X + 4 * NV;        // shared-memory row pitch (floats), multiple of 4
-  static constexpr int SROWS = TH + K - 1;
+  // The TMA unit requires the box start to be 16-byte aligned along x (measured: tools/tma_test.cu), so the
+  // tile starts P4 = roundup(P, 4) columns left of the outputs and every window index is shifted by DELTA.
+  static constexpr int P4 = (P + 3) & ~3;
+  static constexpr int DELTA = P4 - P;
+  static constexpr int NV = (DELTA + K + X - 1 + 3) / 4;   // float4 loads per window row
+  static constexpr int SP = TW - X + 4 * NV;        // shared-memory row pitch (floats) == TMA box width
+  static constexpr int SROWS = TH + K - 1;          // TMA box height
   static constexpr int KP = (K + 3) & ~3;           // padded tap-row length
-  static constexpr int SMEM_FLOATS = SROWS * SP + K * KP;
-  static constexpr size_t SMEM_BYTES = size_t(SMEM_FLOATS) * sizeof(float);
+  static constexpr int IN_BYTES = SROWS * SP * 4;
+  static constexpr int IN_STRIDE = align128(IN_BYTES);
+  static constexpr int EPI_BYTES = TH * TW * 4;     // one epilogue operand tile
+  static constexpr int W_BYTES = align128(K * KP * 4);
+  // [in0][in1][epi0][epi1 (adjoint only)][weights][3 mbarriers]
+  static constexpr int smem_bytes(bool adj) { return 2 * IN_STRIDE + (adj ? 2 : 1) * EPI_BYTES + W_BYTES + 64 + 128; }
 };
-
-// tile(r, c) = plane[Y0 - P + r][X0 - P + c], zero outside [0,Hu) x [0,Wu)
-template <int ROWS, int SP, int THREADS>
-__device__ __forceinline__ void load_tile_zero(float* __restrict__ tile, const float* __restrict__ plane,
-                                               int Hu, int Wu, int pitch, int ytop, int xleft) {
-  for (int idx = threadIdx.x; idx < ROWS * SP; idx += THREADS) {
-    const int r = idx / SP;
-    const int c = idx - r * SP;
-    const int y = ytop + r, x = xleft + c;
-    float v = 0.f;
-    if (y >= 0 && y < Hu && x >= 0 && x < Wu) v = __ldg(plane + size_t(y) * pitch + x);
-    tile[idx] = v;
-  }
-}
 
 // One ky step of the register-blocked stencil: pulls input row (ky + R - 1) of the thread's column window
 // into the rolling register window, loads tap row ky, and issues R * X * K FMAs.
@@ -81,7 +82,7 @@ __device__ __forceinline__ void stencil_step(const float* __restrict__ base, con
 #pragma unroll
     for (int kx = 0; kx < K; ++kx)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) acc[j][i] = fmaf(w[kx], win[(KK + j) % C::R][i + kx], acc[j][i]);
+      for (int i = 0; i < 4; ++i) acc[j][i] = fmaf(w[kx], win[(KK + j) % C::R][i + kx + C::DELTA], acc[j][i]);
 }
 
 template <int K, int KK, int N>
@@ -128,152 +129,184 @@ __device__ __forceinline__ void stencil_core(const float* __restrict__ tile, con
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1 / K4a: err = valid_conv(u, psf) - image       (pyx:477-488 and :557-565)
+// K1 / K4a (ADJ = false): err = valid_conv(u, psf) - image                          pyx:477-488, :557-565
+//     tm_in = u (box SP x SROWS), tm_e0 = image (box TW x TH)
+// K2 (ADJ = true): g = full_conv(err, rot180 psf); max(u_c), max|lambda*g + (u-ut)/2|   pyx:490-491, :519, :524
+//     tm_in = err, tm_e0 = u, tm_e1 = ut
+// Tiles are numbered x-fastest inside a channel; CTA b processes tiles b, b+grid, b+2*grid, ...
 // ------------------------------------------------------------------------------------------------
-template <int K>
+template <int K, bool ADJ>
 __global__ void __launch_bounds__(ConvCfg<K>::THREADS, 2)
-k_conv_fwd(Geom g, State* __restrict__ st, const float* __restrict__ u, const float* __restrict__ img,
-           const float* __restrict__ psf, float* __restrict__ err) {
+k_conv(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_e0,
+       const __grid_constant__ CUtensorMap tm_e1, Geom g, State* __restrict__ st, const float* __restrict__ psf,
+       float lambd, float* __restrict__ out, int ntx, int nty) {
   using C = ConvCfg<K>;
   if (st->stop) return;
-  extern __shared__ float4 smem4[];
-  float* tile = reinterpret_cast<float*>(smem4);
-  float* wS = tile + C::SROWS * C::SP;
-  const int c = blockIdx.z;
-  const int X0 = blockIdx.x * C::TW, Y0 = blockIdx.y * C::TH;
-  // First kernel of an inner step: reset the step-size reductions the adjoint kernel accumulates into
-  // (stream order guarantees the previous update kernel has consumed them).
-  if (blockIdx.x == 0 && blockIdx.y == 0 && c == 0 && threadIdx.x < 3) {
-    st->max_u[threadIdx.x] = 0u;
-    st->max_G[threadIdx.x] = 0u;
-  }
-  // true convolution == correlation with the 180-degree rotated PSF (pyx:242-252 does this on the CPU)
-  for (int i = threadIdx.x; i < K * C::KP; i += C::THREADS) {
-    const int ky = i / C::KP, kx = i - ky * C::KP;
-    wS[i] = (kx < K) ? __ldg(psf + size_t(c) * K * K + (K - 1 - ky) * K + (K - 1 - kx)) : 0.f;
-  }
-  const float* up = u + size_t(c) * g.plane;
-  load_tile_zero<C::SROWS, C::SP, C::THREADS>(tile, up, g.Hu, g.Wu, g.pitch, Y0 - C::P, X0 - C::P);
-  __syncthreads();
-  float acc[C::R][4];
-  stencil_core<K>(tile, wS, acc);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int X = X0 + 4 * lane;
-  if (X >= g.pitch) return;
-  const float* ip = img + size_t(c) * g.plane;
-  float* ep = err + size_t(c) * g.plane;
-#pragma unroll
-  for (int j = 0; j < C::R; ++j) {
-    const int Y = Y0 + warp * C::R + j;
-    if (Y >= g.Hu) break;
-    const bool rowin = (Y >= C::P) && (Y < C::P + g.M);
-    const float4 iv = *reinterpret_cast<const float4*>(ip + size_t(Y) * g.pitch + X);
-    float4 o;
-    o.x = (rowin && X + 0 >= C::P && X + 0 < C::P + g.N) ? acc[j][0] - iv.x : 0.f;
-    o.y = (rowin && X + 1 >= C::P && X + 1 < C::P + g.N) ? acc[j][1] - iv.y : 0.f;
-    o.z = (rowin && X + 2 >= C::P && X + 2 < C::P + g.N) ? acc[j][2] - iv.z : 0.f;
-    o.w = (rowin && X + 3 >= C::P && X + 3 < C::P + g.N) ? acc[j][3] - iv.w : 0.f;
-    *reinterpret_cast<float4*>(ep + size_t(Y) * g.pitch + X) = o;
-  }
-}
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);   // TMA destinations: 128-byte aligned
+  float* in_s[2] = {reinterpret_cast<float*>(smem), reinterpret_cast<float*>(smem + C::IN_STRIDE)};
+  float* e0 = reinterpret_cast<float*>(smem + 2 * C::IN_STRIDE);
+  float* e1 = reinterpret_cast<float*>(smem + 2 * C::IN_STRIDE + C::EPI_BYTES);
+  float* wS = reinterpret_cast<float*>(smem + 2 * C::IN_STRIDE + (ADJ ? 2 : 1) * C::EPI_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * C::IN_STRIDE + (ADJ ? 2 : 1) * C::EPI_BYTES + C::W_BYTES);
+  // bars[0], bars[1]: input stages; bars[2]: epilogue operands
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tiles_per_c = ntx * nty, ntiles = 3 * tiles_per_c;
 
-// ------------------------------------------------------------------------------------------------
-// K2: g = full_conv(err, rot180(psf)); per-channel max(u), max|lambda*g + (u-ut)/2|   (pyx:490-491, :519, :524)
-// ------------------------------------------------------------------------------------------------
-template <int K>
-__global__ void __launch_bounds__(ConvCfg<K>::THREADS, 2)
-k_conv_adj(Geom g, State* __restrict__ st, const float* __restrict__ err, const float* __restrict__ psf,
-           const float* __restrict__ u, const float* __restrict__ ut, float lambd, float* __restrict__ gout) {
-  using C = ConvCfg<K>;
-  if (st->stop) return;
-  extern __shared__ float4 smem4[];
-  float* tile = reinterpret_cast<float*>(smem4);
-  float* wS = tile + C::SROWS * C::SP;
-  __shared__ float red_u[C::WARPS], red_G[C::WARPS];
-  const int c = blockIdx.z;
-  const int X0 = blockIdx.x * C::TW, Y0 = blockIdx.y * C::TH;
-  for (int i = threadIdx.x; i < K * C::KP; i += C::THREADS) {
-    const int ky = i / C::KP, kx = i - ky * C::KP;
-    wS[i] = (kx < K) ? __ldg(psf + size_t(c) * K * K + ky * K + kx) : 0.f;
+  if (!ADJ && blockIdx.x == 0 && tid < 3) {
+    // first kernel of an inner step: reset the step-size reductions the adjoint kernel accumulates into
+    st->max_u[tid] = 0u;
+    st->max_G[tid] = 0u;
   }
-  load_tile_zero<C::SROWS, C::SP, C::THREADS>(tile, err + size_t(c) * g.plane, g.Hu, g.Wu, g.pitch, Y0 - C::P, X0 - C::P);
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&tm_in);
+    tma_prefetch_desc(&tm_e0);
+    if (ADJ) tma_prefetch_desc(&tm_e1);
+  }
   __syncthreads();
-  float acc[C::R][4];
-  stencil_core<K>(tile, wS, acc);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int X = X0 + 4 * lane;
+
+  auto issue_in = [&](int t, int s) {
+    const int c = t / tiles_per_c, r = t - c * tiles_per_c;
+    const int by = r / ntx, bx = r - by * ntx;
+    mbar_arrive_expect_tx(&bars[s], C::IN_BYTES);
+    tma_load_3d(in_s[s], &tm_in, bx * C::TW - C::P4, by * C::TH - C::P, c, &bars[s]);
+  };
+  auto issue_epi = [&](int t) {
+    const int c = t / tiles_per_c, r = t - c * tiles_per_c;
+    const int by = r / ntx, bx = r - by * ntx;
+    mbar_arrive_expect_tx(&bars[2], (ADJ ? 2 : 1) * C::EPI_BYTES);
+    tma_load_3d(e0, &tm_e0, bx * C::TW, by * C::TH, c, &bars[2]);
+    if (ADJ) tma_load_3d(e1, &tm_e1, bx * C::TW, by * C::TH, c, &bars[2]);
+  };
+
+  int t = blockIdx.x;
+  if (tid == 0 && t < ntiles) issue_in(t, 0);
+  int cur_c = -1;
   float mu = -INFINITY, mG = 0.f;
-  if (X < g.pitch) {
-    const float* up = u + size_t(c) * g.plane;
-    const float* utp = ut + size_t(c) * g.plane;
-    float* gp = gout + size_t(c) * g.plane;
-#pragma unroll
-    for (int j = 0; j < C::R; ++j) {
-      const int Y = Y0 + warp * C::R + j;
-      if (Y >= g.Hu) break;
-      const size_t off = size_t(Y) * g.pitch + X;
-      const float4 uv = *reinterpret_cast<const float4*>(up + off);
-      const float4 tv = *reinterpret_cast<const float4*>(utp + off);
-      const float uu[4] = {uv.x, uv.y, uv.z, uv.w};
-      const float tt[4] = {tv.x, tv.y, tv.z, tv.w};
-      float o[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const bool in = (X + i) < g.Wu;
-        o[i] = in ? acc[j][i] : 0.f;
-        if (in) {
-          const float G = fmaf(lambd, acc[j][i], 0.5f * (uu[i] - tt[i]));   // pyx:519
-          mu = fmaxf(mu, uu[i]);
-          mG = fmaxf(mG, fabsf(G));
-        }
-      }
-      *reinterpret_cast<float4*>(gp + off) = make_float4(o[0], o[1], o[2], o[3]);
+  for (int k = 0; t < ntiles; ++k, t += gridDim.x) {
+    const int s = k & 1;
+    const int c = t / tiles_per_c, r = t - c * tiles_per_c;
+    const int by = r / ntx, bx = r - by * ntx;
+    if (tid == 0) {
+      // stage s^1 and the epilogue buffers were released by the __syncthreads that ended iteration k-1
+      const int tn = t + gridDim.x;
+      if (tn < ntiles) issue_in(tn, s ^ 1);
+      issue_epi(t);
     }
-  }
-  mu = warp_max(mu);
-  mG = warp_max(mG);
-  if (lane == 0) { red_u[warp] = mu; red_G[warp] = mG; }
-  __syncthreads();
-  if (warp == 0) {
-    mu = lane < C::WARPS ? red_u[lane] : -INFINITY;
-    mG = lane < C::WARPS ? red_G[lane] : 0.f;
-    mu = warp_max(mu);
-    mG = warp_max(mG);
-    if (lane == 0) {
-      atomicMax(&st->max_u[c], f2ord(mu));
-      atomicMax(&st->max_G[c], f2ord(mG));
+    if (c != cur_c) {
+      // forward: true convolution == correlation with the 180-degree rotated PSF (pyx:242-252 on the CPU)
+      for (int i = tid; i < K * C::KP; i += C::THREADS) {
+        const int ky = i / C::KP, kx = i - ky * C::KP;
+        const int src = ADJ ? (ky * K + kx) : ((K - 1 - ky) * K + (K - 1 - kx));
+        wS[i] = (kx < K) ? __ldg(psf + size_t(c) * K * K + src) : 0.f;
+      }
+      cur_c = c;
+      __syncthreads();
+    }
+    mbar_wait(&bars[s], (k >> 1) & 1);
+    float acc[C::R][4];
+    stencil_core<K>(in_s[s], wS, acc);
+    mbar_wait(&bars[2], k & 1);
+
+    const int X = bx * C::TW + 4 * lane;
+    if (X < g.pitch) {
+      float* op = out + size_t(c) * g.plane;
+#pragma unroll
+      for (int j = 0; j < C::R; ++j) {
+        const int Y = by * C::TH + warp * C::R + j;
+        if (Y >= g.Hu) break;
+        const float4 a = *reinterpret_cast<const float4*>(e0 + (warp * C::R + j) * C::TW + 4 * lane);
+        const float av[4] = {a.x, a.y, a.z, a.w};
+        float o[4];
+        if (!ADJ) {
+          const bool rowin = (Y >= C::P) && (Y < C::P + g.M);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            o[i] = (rowin && (X + i) >= C::P && (X + i) < C::P + g.N) ? acc[j][i] - av[i] : 0.f;
+        } else {
+          const float4 b = *reinterpret_cast<const float4*>(e1 + (warp * C::R + j) * C::TW + 4 * lane);
+          const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const bool in = (X + i) < g.Wu;
+            o[i] = in ? acc[j][i] : 0.f;
+            if (in) {
+              const float G = fmaf(lambd, acc[j][i], 0.5f * (av[i] - bv[i]));   // pyx:519
+              mu = fmaxf(mu, av[i]);
+              mG = fmaxf(mG, fabsf(G));
+            }
+          }
+        }
+        *reinterpret_cast<float4*>(op + size_t(Y) * g.pitch + X) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    }
+    __syncthreads();   // everyone is done with in_s[s], e0, e1 (and wS if the channel changes next)
+    if (ADJ) {
+      // channel boundary (or last tile): flush the per-channel statistics
+      const int tn = t + gridDim.x;
+      const int cn = tn < ntiles ? tn / tiles_per_c : -1;
+      if (cn != c) {
+        __shared__ float red_u[C::WARPS], red_G[C::WARPS];
+        const float wu = warp_max(mu), wG = warp_max(mG);
+        if (lane == 0) { red_u[warp] = wu; red_G[warp] = wG; }
+        __syncthreads();
+        if (warp == 0) {
+          float a = lane < C::WARPS ? red_u[lane] : -INFINITY;
+          float b = lane < C::WARPS ? red_G[lane] : 0.f;
+          a = warp_max(a);
+          b = warp_max(b);
+          if (lane == 0) {
+            atomicMax(&st->max_u[c], f2ord(a));
+            atomicMax(&st->max_G[c], f2ord(b));
+          }
+        }
+        __syncthreads();
+        mu = -INFINITY;
+        mG = 0.f;
+      }
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // K4b: PSF gradient.  gk'[dy][dx] = sum_{Y,X} err[Y][X] * u[Y-P+dy][X-P+dx];  gradk[q] = gk'[K-1-q].
-// Each lane owns a 4-pixel segment of the tile row, each warp a group of DYG displacement rows dy; the
-// DYG*K accumulators per lane are reduced across lanes through shared memory, and each block writes one
-// deterministic partial per (dy,dx) that k_gradk_reduce / k_psf_update sum in a fixed order.
+// Each lane owns a 4-pixel segment of the tile row, each warp a group of DYG displacement rows dy (and one
+// of RP row-parts of the tile).  The DYG*K accumulators per lane PERSIST across all the tiles a CTA walks for
+// one (channel, dy-chunk) work item and are reduced once (xor-butterfly over lanes, fixed-order sum over
+// row-parts); k_gradk_reduce / k_psf_update then sum the per-CTA partials in a fixed order: bit-reproducible.
 // ------------------------------------------------------------------------------------------------
 template <int K>
 struct GradkCfg {
   static constexpr int P = K / 2;
   static constexpr int DYG = (K <= 17) ? 3 : 1;                  // displacement rows per thread
   static constexpr int NG = (K + DYG - 1) / DYG;                 // groups needed to cover all dy
-  static constexpr int NGB = (K <= 17) ? NG : 8;                 // groups (warps per row-part) in one block
-  static constexpr int DYB = NGB * DYG;                          // dy handled by one block
-  static constexpr int NCHUNK = (K + DYB - 1) / DYB;             // blocks along dy
-  static constexpr int RP = (K > 17) ? 1 : (NG >= 5 ? 1 : (NG >= 3 ? 2 : (NG == 2 ? 3 : 4)));
-  static constexpr int RPP = (DYG == 3) ? 30 : 32;               // tile rows per row-part (multiple of DYG)
+  static constexpr int NGB = (K <= 17) ? NG : 8;                 // groups (warps per row-part) in one CTA
+  static constexpr int DYB = NGB * DYG;                          // dy handled per work item
+  static constexpr int NCHUNK = (K + DYB - 1) / DYB;             // work items per channel
+  static constexpr int RP = (K > 17) ? 2 : (NG >= 6 ? 2 : (NG >= 4 ? 3 : (NG == 3 ? 4 : (NG == 2 ? 6 : 12))));
+  static constexpr int RPP = (K > 17) ? 32 : (NG >= 4 ? 30 : (NG == 3 ? 24 : (NG == 2 ? 15 : 6)));
   static constexpr int TH = RP * RPP;
   static constexpr int TW = 128;
-  static constexpr int NV = (K + 3 + 3) / 4;
+  static constexpr int P4 = (P + 3) & ~3;                        // 16-byte aligned TMA box start (see ConvCfg)
+  static constexpr int DELTA = P4 - P;
+  static constexpr int NV = (DELTA + K + 3 + 3) / 4;
   static constexpr int SP = TW - 4 + 4 * NV;
   static constexpr int SROWS = TH + DYB - 1;
   static constexpr int WARPS = NGB * RP;
   static constexpr int THREADS = 32 * WARPS;
-  static constexpr int RSTRIDE = 36;                             // scratch row stride (floats): conflict-free float4 reads
-  static constexpr int TILE_FLOATS = SROWS * SP + TH * TW;
-  static constexpr int SCRATCH_FLOATS = WARPS * DYG * K * RSTRIDE;
-  static constexpr int SMEM_FLOATS = TILE_FLOATS > SCRATCH_FLOATS ? TILE_FLOATS : SCRATCH_FLOATS;
-  static constexpr size_t SMEM_BYTES = size_t(SMEM_FLOATS) * sizeof(float);
+  static constexpr int U_BYTES = SROWS * SP * 4;
+  static constexpr int U_STRIDE = align128(U_BYTES);
+  static constexpr int E_BYTES = TH * TW * 4;
+  static constexpr int STAGE = U_STRIDE + E_BYTES;               // E_BYTES is a multiple of 128
+  static constexpr int RED_BYTES = align128(WARPS * DYG * K * 4);
+  static constexpr int SMEM_BYTES = 2 * STAGE + RED_BYTES + 64 + 128;
+  static_assert(RPP % DYG == 0, "row-part height must be a multiple of the rolling-window depth");
+  static_assert(SMEM_BYTES <= 227 * 1024, "tile does not fit shared memory");
+  static_assert(WARPS <= 16, "too many warps");
 };
 
 template <int K, int KK>
@@ -299,7 +332,7 @@ __device__ __forceinline__ void gradk_step(const float* __restrict__ ubase, cons
 #pragma unroll
     for (int dx = 0; dx < K; ++dx)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) acc[d][dx] = fmaf(e[i], win[(KK + d) % C::DYG][i + dx], acc[d][dx]);
+      for (int i = 0; i < 4; ++i) acc[d][dx] = fmaf(e[i], win[(KK + d) % C::DYG][i + dx + C::DELTA], acc[d][dx]);
 }
 
 template <int K, int KK, int N>
@@ -318,84 +351,120 @@ struct GradkUnroll<K, N, N> {
                                              float (&)[GradkCfg<K>::DYG][K]) {}
 };
 
-// partial layout: [c][tile][dy][dx], tile = blockIdx.y * gridDim.x + blockIdx.x; grid.z = 3 * NCHUNK
+// tm_u: u, box SP x SROWS;  tm_e: err, box TW x TH.  partial layout: [c][cta][dy][dx] (gridDim.x CTAs).
 template <int K>
-__global__ void __launch_bounds__(GradkCfg<K>::THREADS, (GradkCfg<K>::THREADS <= 256) ? 2 : 1)
-k_gradk(Geom g, const State* __restrict__ st, const float* __restrict__ err, const float* __restrict__ u,
-        float* __restrict__ partial) {
+__global__ void __launch_bounds__(GradkCfg<K>::THREADS, 1)
+k_gradk(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_e, Geom g,
+        const State* __restrict__ st, float* __restrict__ partial, int ntx, int nty) {
   using C = GradkCfg<K>;
   if (st->stop) return;
-  extern __shared__ float4 smem4[];
-  float* utile = reinterpret_cast<float*>(smem4);
-  float* etile = utile + C::SROWS * C::SP;
-  const int c = blockIdx.z / C::NCHUNK;
-  const int dyb = (blockIdx.z - c * C::NCHUNK) * C::DYB;
-  const int X0 = blockIdx.x * C::TW, Y0 = blockIdx.y * C::TH;
-  load_tile_zero<C::SROWS, C::SP, C::THREADS>(utile, u + size_t(c) * g.plane, g.Hu, g.Wu, g.pitch,
-                                              Y0 - C::P + dyb, X0 - C::P);
-  load_tile_zero<C::TH, C::TW, C::THREADS>(etile, err + size_t(c) * g.plane, g.Hu, g.Wu, g.pitch, Y0, X0);
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);   // TMA destinations: 128-byte aligned
+  float* u_s[2] = {reinterpret_cast<float*>(smem), reinterpret_cast<float*>(smem + C::STAGE)};
+  float* e_s[2] = {reinterpret_cast<float*>(smem + C::U_STRIDE), reinterpret_cast<float*>(smem + C::STAGE + C::U_STRIDE)};
+  float* red = reinterpret_cast<float*>(smem + 2 * C::STAGE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * C::STAGE + C::RED_BYTES);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int grp = warp % C::NGB, part = warp / C::NGB;
+  const int tiles_per_c = ntx * nty;
+  // tiles of one work item walked by this CTA: b, b+grid, ...
+  const int my_tiles = (tiles_per_c > int(blockIdx.x)) ? (tiles_per_c - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x) : 0;
+  constexpr int NITEMS = 3 * C::NCHUNK;
+  const int total = NITEMS * my_tiles;
+
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&tm_u);
+    tma_prefetch_desc(&tm_e);
+  }
+  __syncthreads();
+
+  auto issue = [&](int q, int s) {
+    const int item = q / my_tiles, tl = blockIdx.x + (q - item * my_tiles) * gridDim.x;
+    const int c = item / C::NCHUNK, dyb = (item - c * C::NCHUNK) * C::DYB;
+    const int by = tl / ntx, bx = tl - by * ntx;
+    mbar_arrive_expect_tx(&bars[s], C::U_BYTES + C::E_BYTES);
+    tma_load_3d(u_s[s], &tm_u, bx * C::TW - C::P4, by * C::TH - C::P + dyb, c, &bars[s]);
+    tma_load_3d(e_s[s], &tm_e, bx * C::TW, by * C::TH, c, &bars[s]);
+  };
+
   float acc[C::DYG][K];
 #pragma unroll
   for (int d = 0; d < C::DYG; ++d)
 #pragma unroll
     for (int dx = 0; dx < K; ++dx) acc[d][dx] = 0.f;
-  {
-    const float* ubase = utile + (part * C::RPP + grp * C::DYG) * C::SP + 4 * lane;
-    const float* ebase = etile + (part * C::RPP) * C::TW + 4 * lane;
-    float win[C::DYG][4 * C::NV];
+
+  if (tid == 0 && total > 0) issue(0, 0);
+  for (int q = 0; q < total; ++q) {
+    const int s = q & 1;
+    if (tid == 0 && q + 1 < total) issue(q + 1, s ^ 1);   // stage s^1 was released by the barrier ending iteration q-1
+    mbar_wait(&bars[s], (q >> 1) & 1);
+    {
+      const float* ubase = u_s[s] + (part * C::RPP + grp * C::DYG) * C::SP + 4 * lane;
+      const float* ebase = e_s[s] + (part * C::RPP) * C::TW + 4 * lane;
+      float win[C::DYG][4 * C::NV];
 #pragma unroll
-    for (int j = 0; j < C::DYG - 1; ++j) {
-      const float4* p = reinterpret_cast<const float4*>(ubase + j * C::SP);
+      for (int j = 0; j < C::DYG - 1; ++j) {
+        const float4* p = reinterpret_cast<const float4*>(ubase + j * C::SP);
 #pragma unroll
-      for (int v = 0; v < C::NV; ++v) {
-        const float4 t = p[v];
-        win[j][4 * v + 0] = t.x; win[j][4 * v + 1] = t.y; win[j][4 * v + 2] = t.z; win[j][4 * v + 3] = t.w;
+        for (int v = 0; v < C::NV; ++v) {
+          const float4 t = p[v];
+          win[j][4 * v + 0] = t.x; win[j][4 * v + 1] = t.y; win[j][4 * v + 2] = t.z; win[j][4 * v + 3] = t.w;
+        }
       }
-    }
 #pragma unroll 1
-    for (int yb = 0; yb < C::RPP; yb += C::DYG) GradkUnroll<K, 0, C::DYG>::run(ubase, ebase, yb, win, acc);
-  }
-  __syncthreads();   // all warps are done with the tiles: reuse the memory as reduction scratch
-  float* scratch = reinterpret_cast<float*>(smem4);
+      for (int yb = 0; yb < C::RPP; yb += C::DYG) GradkUnroll<K, 0, C::DYG>::run(ubase, ebase, yb, win, acc);
+    }
+    const int item = q / my_tiles;
+    const bool last_of_item = (q + 1 == total) || ((q + 1) / my_tiles != item);
+    if (last_of_item) {
+      // reduce over lanes (fixed butterfly), then over row-parts in order, and write this CTA's partial
 #pragma unroll
-  for (int d = 0; d < C::DYG; ++d)
+      for (int d = 0; d < C::DYG; ++d)
 #pragma unroll
-    for (int dx = 0; dx < K; ++dx) scratch[(warp * C::DYG * K + d * K + dx) * C::RSTRIDE + lane] = acc[d][dx];
-  __syncthreads();
-  const int tile = blockIdx.y * gridDim.x + blockIdx.x;
-  const int ntiles = gridDim.x * gridDim.y;
-  for (int o = threadIdx.x; o < C::DYB * K; o += C::THREADS) {
-    const int ld = o / K, dx = o - ld * K;
-    const int dy = dyb + ld;
-    if (dy >= K) continue;
-    const int grp2 = ld / C::DYG, d = ld - grp2 * C::DYG;
-    float s = 0.f;
-    for (int p = 0; p < C::RP; ++p) {
-      const float4* row = reinterpret_cast<const float4*>(scratch + ((p * C::NGB + grp2) * C::DYG * K + d * K + dx) * C::RSTRIDE);
+        for (int dx = 0; dx < K; ++dx) {
+          float v = acc[d][dx];
 #pragma unroll
-      for (int v = 0; v < 8; ++v) {
-        const float4 t = row[v];
-        s += (t.x + t.y) + (t.z + t.w);
+          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          if (lane == 0) red[(warp * C::DYG + d) * K + dx] = v;
+          acc[d][dx] = 0.f;
+        }
+      __syncthreads();
+      const int c = item / C::NCHUNK, dyb = (item - c * C::NCHUNK) * C::DYB;
+      for (int o = tid; o < C::DYB * K; o += C::THREADS) {
+        const int ld = o / K, dx = o - ld * K;
+        const int dy = dyb + ld;
+        if (dy >= K) continue;
+        const int g2 = ld / C::DYG, d = ld - g2 * C::DYG;
+        float sum = 0.f;
+        for (int p = 0; p < C::RP; ++p) sum += red[((p * C::NGB + g2) * C::DYG + d) * K + dx];
+        partial[((size_t(c) * gridDim.x + blockIdx.x) * K + dy) * K + dx] = sum;
       }
     }
-    partial[((size_t(c) * ntiles + tile) * K + dy) * K + dx] = s;
+    __syncthreads();   // stage s (and `red`) free for reuse
+  }
+  if (total == 0) {
+    // CTA without tiles: its partial slots must still be defined (zero)
+    for (int o = tid; o < 3 * K * K; o += C::THREADS) {
+      const int c = o / (K * K), r = o - c * K * K;
+      partial[(size_t(c) * gridDim.x + blockIdx.x) * K * K + r] = 0.f;
+    }
   }
 }
 
-// Stage 1 of the cross-tile reduction: partial2[c][chunk][o] = sum over the chunk's tiles (double).
+// Stage 1 of the cross-CTA reduction: partial2[c][chunk][o] = sum over the chunk's CTA partials (double).
 template <int NCH>
-__global__ void k_gradk_reduce(const State* __restrict__ st, const float* __restrict__ partial, int ntiles, int KK2,
+__global__ void k_gradk_reduce(const State* __restrict__ st, const float* __restrict__ partial, int nparts, int KK2,
                                double* __restrict__ partial2) {
   if (st->stop) return;
   const int c = blockIdx.y, chunk = blockIdx.x;
-  const int per = (ntiles + NCH - 1) / NCH;
-  const int t0 = chunk * per, t1 = min(ntiles, t0 + per);
+  const int per = (nparts + NCH - 1) / NCH;
+  const int t0 = chunk * per, t1 = min(nparts, t0 + per);
   for (int o = threadIdx.x; o < KK2; o += blockDim.x) {
     double s = 0.0;
-    for (int t = t0; t < t1; ++t) s += double(partial[(size_t(c) * ntiles + t) * KK2 + o]);
+    for (int t = t0; t < t1; ++t) s += double(partial[(size_t(c) * nparts + t) * KK2 + o]);
     partial2[(size_t(c) * NCH + chunk) * KK2 + o] = s;
   }
 }
