@@ -144,7 +144,8 @@ k_conv(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtens
   if (st->stop) return;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);   // TMA destinations: 128-byte aligned
-  float* in_s[2] = {reinterpret_cast<float*>(smem), reinterpret_cast<float*>(smem + C::IN_STRIDE)};
+  // NB: stage buffers are addressed as smem + s * stride (never through a pointer array): the compiler must
+  // see shared-space provenance to emit LDS.128 instead of generic LD.E (measured: 4x shared wavefronts).
   float* e0 = reinterpret_cast<float*>(smem + 2 * C::IN_STRIDE);
   float* e1 = reinterpret_cast<float*>(smem + 2 * C::IN_STRIDE + C::EPI_BYTES);
   float* wS = reinterpret_cast<float*>(smem + 2 * C::IN_STRIDE + (ADJ ? 2 : 1) * C::EPI_BYTES);
@@ -173,7 +174,7 @@ k_conv(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtens
     const int c = t / tiles_per_c, r = t - c * tiles_per_c;
     const int by = r / ntx, bx = r - by * ntx;
     mbar_arrive_expect_tx(&bars[s], C::IN_BYTES);
-    tma_load_3d(in_s[s], &tm_in, bx * C::TW - C::P4, by * C::TH - C::P, c, &bars[s]);
+    tma_load_3d(smem + s * C::IN_STRIDE, &tm_in, bx * C::TW - C::P4, by * C::TH - C::P, c, &bars[s]);
   };
   auto issue_epi = [&](int t) {
     const int c = t / tiles_per_c, r = t - c * tiles_per_c;
@@ -209,7 +210,7 @@ k_conv(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtens
     }
     mbar_wait(&bars[s], (k >> 1) & 1);
     float acc[C::R][4];
-    stencil_core<K>(in_s[s], wS, acc);
+    stencil_core<K>(reinterpret_cast<const float*>(smem + s * C::IN_STRIDE), wS, acc);
     mbar_wait(&bars[2], k & 1);
 
     const int X = bx * C::TW + 4 * lane;
@@ -244,7 +245,7 @@ k_conv(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtens
         *reinterpret_cast<float4*>(op + size_t(Y) * g.pitch + X) = make_float4(o[0], o[1], o[2], o[3]);
       }
     }
-    __syncthreads();   // everyone is done with in_s[s], e0, e1 (and wS if the channel changes next)
+    __syncthreads();   // everyone is done with stage s, e0, e1 (and wS if the channel changes next)
     if (ADJ) {
       // channel boundary (or last tile): flush the per-channel statistics
       const int tn = t + gridDim.x;
@@ -360,8 +361,8 @@ k_gradk(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtens
   if (st->stop) return;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);   // TMA destinations: 128-byte aligned
-  float* u_s[2] = {reinterpret_cast<float*>(smem), reinterpret_cast<float*>(smem + C::STAGE)};
-  float* e_s[2] = {reinterpret_cast<float*>(smem + C::U_STRIDE), reinterpret_cast<float*>(smem + C::STAGE + C::U_STRIDE)};
+  // stage s: u tile at smem + s*STAGE, err tile at smem + s*STAGE + U_STRIDE (pointer arithmetic, not a
+  // pointer array, so the loads stay LDS)
   float* red = reinterpret_cast<float*>(smem + 2 * C::STAGE);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * C::STAGE + C::RED_BYTES);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -386,8 +387,8 @@ k_gradk(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtens
     const int c = item / C::NCHUNK, dyb = (item - c * C::NCHUNK) * C::DYB;
     const int by = tl / ntx, bx = tl - by * ntx;
     mbar_arrive_expect_tx(&bars[s], C::U_BYTES + C::E_BYTES);
-    tma_load_3d(u_s[s], &tm_u, bx * C::TW - C::P4, by * C::TH - C::P + dyb, c, &bars[s]);
-    tma_load_3d(e_s[s], &tm_e, bx * C::TW, by * C::TH, c, &bars[s]);
+    tma_load_3d(smem + s * C::STAGE, &tm_u, bx * C::TW - C::P4, by * C::TH - C::P + dyb, c, &bars[s]);
+    tma_load_3d(smem + s * C::STAGE + C::U_STRIDE, &tm_e, bx * C::TW, by * C::TH, c, &bars[s]);
   };
 
   float acc[C::DYG][K];
@@ -402,8 +403,8 @@ k_gradk(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtens
     if (tid == 0 && q + 1 < total) issue(q + 1, s ^ 1);   // stage s^1 was released by the barrier ending iteration q-1
     mbar_wait(&bars[s], (q >> 1) & 1);
     {
-      const float* ubase = u_s[s] + (part * C::RPP + grp * C::DYG) * C::SP + 4 * lane;
-      const float* ebase = e_s[s] + (part * C::RPP) * C::TW + 4 * lane;
+      const float* ubase = reinterpret_cast<const float*>(smem + s * C::STAGE) + (part * C::RPP + grp * C::DYG) * C::SP + 4 * lane;
+      const float* ebase = reinterpret_cast<const float*>(smem + s * C::STAGE + C::U_STRIDE) + (part * C::RPP) * C::TW + 4 * lane;
       float win[C::DYG][4 * C::NV];
 #pragma unroll
       for (int j = 0; j < C::DYG - 1; ++j) {
