@@ -37,6 +37,12 @@ class Stats(C.Structure):
                     M_r_history=[float(self.M_r_history[i]) for i in range(int(self.n_history))])
 
 
+class Band(C.Structure):
+    _fields_ = [("row_lo", C.c_int32), ("row_hi", C.c_int32), ("own_lo", C.c_int32), ("own_hi", C.c_int32)]
+
+
+PH_OUTER_BEGIN, PH_GRAD, PH_UPDATE, PH_PSF_GRAD, PH_PSF_STEP, PH_OUTER_END = range(6)
+
 # every symbol include/rltv_b200.h declares: (name, restype, argtypes)
 _FP = C.POINTER(C.c_float)
 SYMBOLS = [
@@ -57,6 +63,16 @@ SYMBOLS = [
     ("rltv_stream", C.c_void_p, [C.c_void_p]),
     ("rltv_profile_enable", C.c_int, [C.c_void_p, C.c_int32]),
     ("rltv_profile_get", C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
+    ("rltv_create_band", C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(Band), C.c_void_p]),
+    ("rltv_upload_band", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),
+    ("rltv_download_rows", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    ("rltv_ipc_export", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("rltv_ipc_attach", C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32]),
+    ("rltv_set_whiteness_owner", C.c_int, [C.c_void_p, C.c_int32]),
+    ("rltv_enqueue_phase", C.c_int, [C.c_void_p, C.c_int32]),
+    ("rltv_device_ptr", C.c_void_p, [C.c_void_p, C.c_char_p, C.POINTER(C.c_size_t)]),
+    ("rltv_poll_record", C.c_int, [C.c_void_p, C.c_int32]),
+    ("rltv_poll_wait", C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]),
     ("rltv_stage_residual", C.c_int, [C.c_void_p, C.c_void_p]),
     ("rltv_stage_adjoint", C.c_int, [C.c_void_p, C.c_void_p]),
     ("rltv_stage_gradk", C.c_int, [C.c_void_p, C.c_void_p]),

@@ -1,21 +1,26 @@
 // Host side of the C ABI declared in include/rltv_b200.h: context, buffers, launch sequencing.
 // One inner step of the reference (lib/deconvolution.pyx:473-591) is the kernel sequence
-//   k_conv_fwd -> k_conv_adj -> k_update [-> k_conv_fwd -> k_gradk -> k_gradk_reduce -> k_psf_update]
+//   GRAD     : k_conv<K,fwd> -> k_conv<K,adj>                         (pyx:477-491, :519, :524)
+//   UPDATE   : k_update [-> k_halo_push]                              (pyx:527-531, :499-502, :552)
+//   PSF_GRAD : [k_halo_wait ->] k_conv<K,fwd> -> k_gradk<K> -> reduce (pyx:557-571)
+//   PSF_STEP : k_psf_update                                           (pyx:574-589)
 // and one outer iteration (pyx:460-656) is  ut=u ; 5 inner steps ; whiteness statistic + stop rule.
 // Nothing is read back between kernels: step sizes, the PSF, the statistic and the stop flag live in a
 // device-resident State; once the flag is set every later kernel returns at its first instruction, so the
 // host may run ahead (it polls the flag two outer iterations behind, without draining the stream).
+// With row-band sharding (one context per GPU) the host all-reduces three tiny device buffers between
+// phases (step_max, gk_sum, stop); halos move by peer stores inside k_halo_push.
 #include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <cmath>
 #include <cstdio>
 #include <cstring>
-#include <map>
 #include <string>
 #include <vector>
 
 #include "../../include/rltv_b200.h"
+#include "rltv_band.cuh"
 #include "rltv_common.cuh"
 #include "rltv_elementwise.cuh"
 #include "rltv_stencil.cuh"
@@ -26,7 +31,7 @@ using namespace rltv;
 namespace {
 
 thread_local std::string g_err;
-constexpr int NCH = 64;  // chunks of the cross-tile PSF-gradient reduction
+constexpr int NCH = 64;  // chunks of the cross-CTA PSF-gradient reduction
 
 int fail(int code, const std::string& msg) {
   g_err = msg;
@@ -40,8 +45,8 @@ int fail(int code, const std::string& msg) {
       return fail(RLTV_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));             \
   } while (0)
 
-enum Family { F_CONV_FWD = 0, F_CONV_ADJ, F_UPDATE, F_GRADK, F_PSF, F_STATS, F_COPY, F_COUNT };
-const char* kFamilyNames[F_COUNT] = {"conv_fwd", "conv_adj", "update", "gradk", "psf", "stats", "copy"};
+enum Family { F_CONV_FWD = 0, F_CONV_ADJ, F_UPDATE, F_GRADK, F_PSF, F_STATS, F_COPY, F_HALO, F_COUNT };
+const char* kFamilyNames[F_COUNT] = {"conv_fwd", "conv_adj", "update", "gradk", "psf", "stats", "copy", "halo"};
 
 }  // namespace
 
@@ -50,7 +55,11 @@ struct rltv_ctx {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   Geom g{};
+  int row_lo = 0, row_hi = 0, own_lo = 0, own_hi = 0;   // frame coordinates (rows of u)
+  int fwd0 = 0, fwd1 = 0;                               // local rows on which the residual is computed
+  bool banded = false;
   float *u = nullptr, *ut = nullptr, *gbuf = nullptr, *img = nullptr, *err = nullptr;
+  size_t u_alloc_bytes = 0, flag_offset = 0;            // u allocation also carries the two halo flags
   float* staging = nullptr;
   float *psf = nullptr, *psf_caller = nullptr, *psf_hwc = nullptr;
   State* st = nullptr;
@@ -60,10 +69,16 @@ struct rltv_ctx {
   float* gk_partial = nullptr;
   int gk_nparts = 0;            // CTAs of the persistent k_gradk grid (one partial each)
   int num_sms = 148;
-  // TMA descriptors (rank-3 tensors x: Wu, y: Hu, c: 3 over the planar arrays; boxes per kernel)
+  // TMA descriptors (rank-3 tensors x: Wu, y: rows, c: 3 over the planar arrays; boxes per kernel)
   CUtensorMap tm_u_conv{}, tm_err_conv{}, tm_img_epi{}, tm_u_epi{}, tm_ut_epi{}, tm_u_gk{}, tm_err_gk{};
-  double* gk_partial2 = nullptr;
-  float* gk_out = nullptr;
+  double *gk_partial2 = nullptr, *gk_sum = nullptr;
+  // halo exchange
+  HaloSide side[2]{};           // 0: band above, 1: band below
+  void* peer_base[2] = {nullptr, nullptr};
+  unsigned* push_counter = nullptr;
+  int halo_seq = 0;             // pushes issued so far (identical on every band; never reset)
+  bool halo_pending = false;    // a push has been issued since the last wait
+  bool white_owner = true;
   // whiteness
   WhiteGeom wg{};
   double2 *Z = nullptr, *tw = nullptr;
@@ -142,11 +157,12 @@ PFN_tmapEncodeTiled tmap_encoder() {
   return fn;
 }
 
-// rank-3 view (x: Wu, y: Hu, c: 3) of one planar frame array, box = bw x bh x 1, zero fill out of bounds
-int make_tmap(CUtensorMap* tm, float* base, const Geom& g, int bw, int bh) {
+// rank-3 view (x: Wu, y: rows, c: 3) of `rows` rows of one planar frame array starting at `base`,
+// box = bw x bh x 1, zero fill out of bounds
+int make_tmap(CUtensorMap* tm, float* base, const Geom& g, int rows, int bw, int bh) {
   PFN_tmapEncodeTiled enc = tmap_encoder();
   if (!enc) return fail(RLTV_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
-  cuuint64_t dims[3] = {cuuint64_t(g.Wu), cuuint64_t(g.Hu), 3};
+  cuuint64_t dims[3] = {cuuint64_t(g.Wu), cuuint64_t(rows), 3};
   cuuint64_t strides[2] = {cuuint64_t(g.pitch) * 4, cuuint64_t(g.plane) * 4};
   cuuint32_t box[3] = {cuuint32_t(bw), cuuint32_t(bh), 1};
   cuuint32_t estr[3] = {1, 1, 1};
@@ -160,45 +176,44 @@ template <int K>
 int make_maps_t(rltv_ctx* c) {
   using C = ConvCfg<K>;
   using G = GradkCfg<K>;
+  const Geom& g = c->g;
   int rc;
-  if ((rc = make_tmap(&c->tm_u_conv, c->u, c->g, C::SP, C::SROWS))) return rc;
-  if ((rc = make_tmap(&c->tm_err_conv, c->err, c->g, C::SP, C::SROWS))) return rc;
-  if ((rc = make_tmap(&c->tm_img_epi, c->img, c->g, C::TW, C::TH))) return rc;
-  if ((rc = make_tmap(&c->tm_u_epi, c->u, c->g, C::TW, C::TH))) return rc;
-  if ((rc = make_tmap(&c->tm_ut_epi, c->ut, c->g, C::TW, C::TH))) return rc;
-  if ((rc = make_tmap(&c->tm_u_gk, c->u, c->g, G::SP, G::SROWS))) return rc;
-  if ((rc = make_tmap(&c->tm_err_gk, c->err, c->g, G::TW, G::TH))) return rc;
+  if ((rc = make_tmap(&c->tm_u_conv, c->u, g, g.Hu, C::SP, C::SROWS))) return rc;
+  if ((rc = make_tmap(&c->tm_err_conv, c->err, g, g.Hu, C::SP, C::SROWS))) return rc;
+  if ((rc = make_tmap(&c->tm_img_epi, c->img, g, g.Hu, C::TW, C::TH))) return rc;
+  if ((rc = make_tmap(&c->tm_u_epi, c->u, g, g.Hu, C::TW, C::TH))) return rc;
+  if ((rc = make_tmap(&c->tm_ut_epi, c->ut, g, g.Hu, C::TW, C::TH))) return rc;
+  if ((rc = make_tmap(&c->tm_u_gk, c->u, g, g.Hu, G::SP, G::SROWS))) return rc;
+  // residual as seen by the PSF gradient: OWNED rows only (halo rows read as zero)
+  if ((rc = make_tmap(&c->tm_err_gk, c->err + size_t(g.own0) * g.pitch, g, g.own1 - g.own0, G::TW, G::TH))) return rc;
   return RLTV_OK;
 }
 
+// forward residual on local rows [fwd0, fwd1); adjoint on the owned rows
 template <int K, bool ADJ>
 int launch_conv_t(rltv_ctx* c, float lambd) {
   using C = ConvCfg<K>;
   constexpr int SMEM = C::smem_bytes(ADJ);
   CU(cudaFuncSetAttribute(k_conv<K, ADJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-  const int ntx = (c->g.pitch + C::TW - 1) / C::TW, nty = (c->g.Hu + C::TH - 1) / C::TH;
+  const int y0 = ADJ ? c->g.own0 : c->fwd0, y1 = ADJ ? c->g.own1 : c->fwd1;
+  const int ntx = (c->g.pitch + C::TW - 1) / C::TW, nty = (y1 - y0 + C::TH - 1) / C::TH;
   int grid = 2 * c->num_sms;
   if (grid > 3 * ntx * nty) grid = 3 * ntx * nty;
   ProfScope p(c, ADJ ? F_CONV_ADJ : F_CONV_FWD);
   if (ADJ)
     k_conv<K, true><<<grid, C::THREADS, SMEM, c->stream>>>(c->tm_err_conv, c->tm_u_epi, c->tm_ut_epi, c->g, c->st, c->psf,
-                                                          lambd, c->gbuf, ntx, nty);
+                                                          lambd, c->gbuf, ntx, nty, y0, y1);
   else
     k_conv<K, false><<<grid, C::THREADS, SMEM, c->stream>>>(c->tm_u_conv, c->tm_img_epi, c->tm_img_epi, c->g, c->st, c->psf,
-                                                           lambd, c->err, ntx, nty);
+                                                           lambd, c->err, ntx, nty, y0, y1);
   return RLTV_OK;
 }
-
-template <int K>
-int launch_conv_fwd_t(rltv_ctx* c) { return launch_conv_t<K, false>(c, 0.f); }
-template <int K>
-int launch_conv_adj_t(rltv_ctx* c, float lambd) { return launch_conv_t<K, true>(c, lambd); }
 
 template <int K>
 int launch_gradk_t(rltv_ctx* c) {
   using C = GradkCfg<K>;
   CU(cudaFuncSetAttribute(k_gradk<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-  const int ntx = (c->g.Wu + C::TW - 1) / C::TW, nty = (c->g.Hu + C::TH - 1) / C::TH;
+  const int ntx = (c->g.Wu + C::TW - 1) / C::TW, nty = (c->g.own1 - c->g.own0 + C::TH - 1) / C::TH;
   {
     ProfScope p(c, F_GRADK);
     k_gradk<K><<<c->gk_nparts, C::THREADS, C::SMEM_BYTES, c->stream>>>(c->tm_u_gk, c->tm_err_gk, c->g, c->st, c->gk_partial, ntx, nty);
@@ -206,6 +221,10 @@ int launch_gradk_t(rltv_ctx* c) {
   {
     ProfScope p(c, F_GRADK);
     k_gradk_reduce<NCH><<<dim3(NCH, 3), 256, 0, c->stream>>>(c->st, c->gk_partial, c->gk_nparts, K * K, c->gk_partial2);
+  }
+  {
+    ProfScope p(c, F_GRADK);
+    k_gradk_final<NCH><<<(3 * K * K + 255) / 256, 256, 0, c->stream>>>(c->st, c->gk_partial2, K * K, c->gk_sum);
   }
   return RLTV_OK;
 }
@@ -218,10 +237,9 @@ int make_maps(rltv_ctx* c) {
   }
   return fail(RLTV_ERR_ARG, "unsupported MK");
 }
-
 int launch_conv_fwd(rltv_ctx* c) {
   switch (c->g.K) {
-#define M(K_) case K_: return launch_conv_fwd_t<K_>(c);
+#define M(K_) case K_: return launch_conv_t<K_, false>(c, 0.f);
     RLTV_FOR_EACH_K(M)
 #undef M
   }
@@ -229,7 +247,7 @@ int launch_conv_fwd(rltv_ctx* c) {
 }
 int launch_conv_adj(rltv_ctx* c, float lambd) {
   switch (c->g.K) {
-#define M(K_) case K_: return launch_conv_adj_t<K_>(c, lambd);
+#define M(K_) case K_: return launch_conv_t<K_, true>(c, lambd);
     RLTV_FOR_EACH_K(M)
 #undef M
   }
@@ -243,8 +261,9 @@ int launch_gradk(rltv_ctx* c) {
   }
   return fail(RLTV_ERR_ARG, "unsupported MK");
 }
+
 int launch_update(rltv_ctx* c) {
-  dim3 grid((c->g.pitch / 4 + 255) / 256, c->g.Hu, 3);
+  dim3 grid((c->g.pitch / 4 + 255) / 256, c->g.own1 - c->g.own0, 3);
   ProfScope p(c, F_UPDATE);
   k_update<<<grid, 256, 0, c->stream>>>(c->g, c->st, c->u, c->ut, c->gbuf, c->img, c->params.step_factor,
                                         c->params.lambd, c->params.blind);
@@ -254,8 +273,27 @@ int launch_update(rltv_ctx* c) {
 int launch_psf_update(rltv_ctx* c) {
   const int K = c->g.K;
   ProfScope p(c, F_PSF);
-  k_psf_update<NCH><<<1, 256, 6 * K * K * sizeof(float), c->stream>>>(c->st, c->gk_partial2, K, c->params.step_factor,
-                                                                     c->params.correlation, c->psf, c->psf_caller);
+  k_psf_update<<<1, 256, 6 * K * K * sizeof(float), c->stream>>>(c->st, c->gk_sum, K, c->params.step_factor,
+                                                                c->params.correlation, c->psf, c->psf_caller);
+  return RLTV_OK;
+}
+
+int launch_halo_push(rltv_ctx* c) {
+  if (!c->side[0].peer_u && !c->side[1].peer_u) return RLTV_OK;
+  c->halo_seq += 1;
+  c->halo_pending = true;
+  ProfScope p(c, F_HALO);
+  k_halo_push<<<2 * c->num_sms, 256, 0, c->stream>>>(c->g, c->st, c->u, c->side[0], c->side[1], c->push_counter, c->halo_seq);
+  return RLTV_OK;
+}
+
+int launch_halo_wait(rltv_ctx* c) {
+  if (!c->halo_pending) return RLTV_OK;
+  c->halo_pending = false;
+  const int* flags = reinterpret_cast<const int*>(reinterpret_cast<const char*>(c->u) + c->flag_offset);
+  ProfScope p(c, F_HALO);
+  k_halo_wait<<<1, 32, 0, c->stream>>>(c->st, c->side[0].peer_u ? flags + 0 : nullptr,
+                                       c->side[1].peer_u ? flags + 1 : nullptr, c->halo_seq);
   return RLTV_OK;
 }
 
@@ -270,6 +308,11 @@ int setup_whiteness(rltv_ctx* c, int top, int bottom, int left, int right) {
   const int h = bottom - top, w = right - left;
   if (top < 0 || left < 0 || bottom > c->g.M || right > c->g.N || h < 2 || w < 2)
     return fail(RLTV_ERR_ARG, "whiteness window outside the image");
+  if (c->white_owner) {
+    const int l0 = top + c->g.P - c->g.row0, l1 = bottom + c->g.P - c->g.row0;
+    if (l0 < c->fwd0 || l1 > c->fwd1)
+      return fail(RLTV_ERR_ARG, "whiteness window is not inside the rows this band computes the residual on");
+  }
   const int mx = h > w ? h : w;
   int L = next_pow2(mx + (mx + 1) / 2 + 1);
   if (L < 64) L = 64;
@@ -324,16 +367,17 @@ int setup_whiteness(rltv_ctx* c, int top, int bottom, int left, int right) {
 
 int launch_whiteness(rltv_ctx* c, int advance) {
   const WhiteGeom& wg = c->wg;
+  if (!c->white_owner) {
+    ProfScope p(c, F_STATS);
+    k_outer_finalize<<<1, 32, 0, c->stream>>>(c->st, wg, c->rowacc, c->params.blind, c->params.tau, advance, 0, c->mr_out);
+    return RLTV_OK;
+  }
   const int L = wg.L;
   const int fft_threads = L / 2 < 32 ? 32 : L / 2;
   const size_t fft_smem = size_t(L) * sizeof(double2);
-  static bool attr = false;
-  if (!attr) {
-    CU(cudaFuncSetAttribute(k_white_rows_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * 16));
-    CU(cudaFuncSetAttribute(k_white_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * 16));
-    CU(cudaFuncSetAttribute(k_white_rows_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * 16));
-    attr = true;
-  }
+  CU(cudaFuncSetAttribute(k_white_rows_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * 16));
+  CU(cudaFuncSetAttribute(k_white_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * 16));
+  CU(cudaFuncSetAttribute(k_white_rows_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * 16));
   { ProfScope p(c, F_STATS);
     k_win_rows<<<dim3(wg.h, 3), 128, 0, c->stream>>>(c->g, c->st, c->err, wg, c->rowsum, c->rowmin, c->rowmax); }
   { ProfScope p(c, F_STATS);
@@ -345,34 +389,50 @@ int launch_whiteness(rltv_ctx* c, int advance) {
   { ProfScope p(c, F_STATS);
     k_white_rows_inv<<<dim3(wg.h, 3), fft_threads, fft_smem, c->stream>>>(c->st, wg, c->tw, c->Z, c->wa, c->wb, c->rowacc); }
   { ProfScope p(c, F_STATS);
-    k_outer_finalize<<<1, 32, 0, c->stream>>>(c->st, wg, c->rowacc, c->params.blind, c->params.tau, advance, c->mr_out); }
+    k_outer_finalize<<<1, 32, 0, c->stream>>>(c->st, wg, c->rowacc, c->params.blind, c->params.tau, advance, 1, c->mr_out); }
   return RLTV_OK;
 }
 
-int enqueue_inner(rltv_ctx* c) {
-  int rc;
-  if ((rc = launch_conv_fwd(c)) != RLTV_OK) return rc;                    // pyx:477-488
-  if ((rc = launch_conv_adj(c, c->params.lambd)) != RLTV_OK) return rc;   // pyx:490-491, :519, :524
-  if ((rc = launch_update(c)) != RLTV_OK) return rc;                      // pyx:527-531, :499-502, :552
-  if (c->params.blind) {
-    if ((rc = launch_conv_fwd(c)) != RLTV_OK) return rc;                  // pyx:557-565
-    if ((rc = launch_gradk(c)) != RLTV_OK) return rc;                     // pyx:567-571
-    if ((rc = launch_psf_update(c)) != RLTV_OK) return rc;                // pyx:574-589
+int enqueue_phase(rltv_ctx* c, int phase) {
+  int rc = RLTV_OK;
+  switch (phase) {
+    case RLTV_PH_OUTER_BEGIN: {
+      if ((rc = launch_halo_wait(c)) != RLTV_OK) return rc;       // ut must copy refreshed halos
+      ProfScope p(c, F_COPY);                                      // ut[:] = u.copy(), pyx:462
+      CU(cudaMemcpyAsync(c->ut, c->u, 3 * c->g.plane * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+      return RLTV_OK;
+    }
+    case RLTV_PH_GRAD:
+      if ((rc = launch_halo_wait(c)) != RLTV_OK) return rc;
+      if ((rc = launch_conv_fwd(c)) != RLTV_OK) return rc;        // pyx:477-488
+      return launch_conv_adj(c, c->params.lambd);                 // pyx:490-491, :519, :524
+    case RLTV_PH_UPDATE:
+      if ((rc = launch_update(c)) != RLTV_OK) return rc;          // pyx:527-531, :499-502, :552
+      return launch_halo_push(c);
+    case RLTV_PH_PSF_GRAD:
+      if ((rc = launch_halo_wait(c)) != RLTV_OK) return rc;
+      if ((rc = launch_conv_fwd(c)) != RLTV_OK) return rc;        // pyx:557-565
+      return launch_gradk(c);                                     // pyx:567-571
+    case RLTV_PH_PSF_STEP:
+      return launch_psf_update(c);                                // pyx:574-589
+    case RLTV_PH_OUTER_END:
+      return launch_whiteness(c, 1);                              // pyx:623-656
   }
-  return RLTV_OK;
+  return fail(RLTV_ERR_ARG, "unknown phase");
 }
 
 int enqueue_outer(rltv_ctx* c) {
-  {
-    ProfScope p(c, F_COPY);                                               // ut[:] = u.copy(), pyx:462
-    CU(cudaMemcpyAsync(c->ut, c->u, 3 * c->g.plane * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
-  }
+  int rc;
+  if ((rc = enqueue_phase(c, RLTV_PH_OUTER_BEGIN)) != RLTV_OK) return rc;
   for (int i = 0; i < RLTV_INNER_ITER; ++i) {
-    int rc = enqueue_inner(c);
-    if (rc != RLTV_OK) return rc;
+    if ((rc = enqueue_phase(c, RLTV_PH_GRAD)) != RLTV_OK) return rc;
+    if ((rc = enqueue_phase(c, RLTV_PH_UPDATE)) != RLTV_OK) return rc;
+    if (c->params.blind) {
+      if ((rc = enqueue_phase(c, RLTV_PH_PSF_GRAD)) != RLTV_OK) return rc;
+      if ((rc = enqueue_phase(c, RLTV_PH_PSF_STEP)) != RLTV_OK) return rc;
+    }
   }
-  int rc = launch_whiteness(c, 1);
-  if (rc != RLTV_OK) return rc;
+  if ((rc = enqueue_phase(c, RLTV_PH_OUTER_END)) != RLTV_OK) return rc;
   CU(cudaGetLastError());
   return RLTV_OK;
 }
@@ -398,6 +458,11 @@ int check_ctx(rltv_ctx* c) {
   return RLTV_OK;
 }
 
+int hwc_grid(int cols) {
+  const int b = (cols * 3 + 255) / 256;
+  return b > 64 ? 64 : b;
+}
+
 }  // namespace
 
 // =====================================================================================================
@@ -417,12 +482,18 @@ int rltv_device_count(void) {
   return n;
 }
 
-int rltv_create(rltv_ctx** out, int32_t device, int32_t M, int32_t N, int32_t MK, void* stream) {
+int rltv_create_band(rltv_ctx** out, int32_t device, int32_t M, int32_t N, int32_t MK, const rltv_band_t* band, void* stream) {
   if (!out) return fail(RLTV_ERR_ARG, "null out pointer");
   *out = nullptr;
   if (MK < 3 || (MK % 2) == 0 || MK > RLTV_MAX_MK) return fail(RLTV_ERR_ARG, "MK must be odd and in [3, 31]");
   if (M < 1 || N < 1) return fail(RLTV_ERR_ARG, "empty image");
-  if (M + MK - 1 > 65535) return fail(RLTV_ERR_ARG, "more than 65535 padded rows");
+  const int HuG = M + MK - 1, P = MK / 2;
+  rltv_band_t b = band ? *band : rltv_band_t{0, HuG, 0, HuG};
+  if (b.row_lo < 0 || b.row_hi > HuG || b.own_lo < b.row_lo || b.own_hi > b.row_hi || b.own_lo >= b.own_hi)
+    return fail(RLTV_ERR_ARG, "bad row band");
+  if ((b.own_lo > 0 && b.own_lo - b.row_lo < 2 * P) || (b.own_hi < HuG && b.row_hi - b.own_hi < 2 * P))
+    return fail(RLTV_ERR_ARG, "row band needs a halo of 2*(MK/2) rows on every interior side");
+  if (b.row_hi - b.row_lo > 65535) return fail(RLTV_ERR_ARG, "more than 65535 padded rows");
   int ndev = rltv_device_count();
   if (ndev <= 0) return fail(RLTV_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
   if (device < 0 || device >= ndev) return fail(RLTV_ERR_ARG, "bad device index");
@@ -435,13 +506,24 @@ int rltv_create(rltv_ctx** out, int32_t device, int32_t M, int32_t N, int32_t MK
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->own_stream = true;
   }
+  c->row_lo = b.row_lo; c->row_hi = b.row_hi; c->own_lo = b.own_lo; c->own_hi = b.own_hi;
+  c->banded = band != nullptr && !(b.row_lo == 0 && b.row_hi == HuG);
   Geom& g = c->g;
-  g.M = M; g.N = N; g.K = MK; g.P = MK / 2;
-  g.Hu = M + MK - 1; g.Wu = N + MK - 1;
+  g.M = M; g.N = N; g.K = MK; g.P = P;
+  g.Hu = b.row_hi - b.row_lo; g.Wu = N + MK - 1;
   g.pitch = (g.Wu + 3) & ~3;
   g.plane = size_t(g.Hu) * g.pitch;
+  g.row0 = b.row_lo; g.own0 = b.own_lo - b.row_lo; g.own1 = b.own_hi - b.row_lo;
+  // the residual is needed P rows beyond the owned rows (adjoint support); clip to the rows whose own
+  // support (P more rows) is held, or to the frame border where zero fill is the true boundary
+  c->fwd0 = (b.row_lo == 0) ? 0 : g.own0 - P;
+  c->fwd1 = (b.row_hi == HuG) ? g.Hu : g.own1 + P;
   const size_t pb = 3 * g.plane * sizeof(float);
-  float** planes[5] = {&c->u, &c->ut, &c->gbuf, &c->img, &c->err};
+  c->flag_offset = (pb + 255) & ~size_t(255);
+  c->u_alloc_bytes = c->flag_offset + 256;
+  if (cudaMalloc(&c->u, c->u_alloc_bytes) != cudaSuccess) { rltv_destroy(c); return fail(RLTV_ERR_ALLOC, "cudaMalloc of the estimate failed"); }
+  CU(cudaMemsetAsync(c->u, 0, c->u_alloc_bytes, c->stream));
+  float** planes[4] = {&c->ut, &c->gbuf, &c->img, &c->err};
   for (auto p : planes) {
     if (cudaMalloc(p, pb) != cudaSuccess) { rltv_destroy(c); return fail(RLTV_ERR_ALLOC, "cudaMalloc of a frame plane set failed"); }
     CU(cudaMemsetAsync(*p, 0, pb, c->stream));
@@ -451,9 +533,10 @@ int rltv_create(rltv_ctx** out, int32_t device, int32_t M, int32_t N, int32_t MK
   CU(cudaMalloc(&c->psf, kb));
   CU(cudaMalloc(&c->psf_caller, kb));
   CU(cudaMalloc(&c->psf_hwc, kb));
-  CU(cudaMalloc(&c->gk_out, kb));
   CU(cudaMalloc(&c->st, sizeof(State)));
   CU(cudaMemsetAsync(c->st, 0, sizeof(State), c->stream));
+  CU(cudaMalloc(&c->push_counter, sizeof(unsigned)));
+  CU(cudaMemsetAsync(c->push_counter, 0, sizeof(unsigned), c->stream));
   CU(cudaMallocHost(&c->h_st, sizeof(State)));
   CU(cudaMallocHost(&c->h_poll, 4 * 2 * sizeof(int)));
   for (auto& e : c->poll_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -466,26 +549,32 @@ int rltv_create(rltv_ctx** out, int32_t device, int32_t M, int32_t N, int32_t MK
   }
   c->gk_nparts = c->num_sms;   // persistent k_gradk: one CTA per SM, one partial per CTA
   CU(cudaMalloc(&c->gk_partial, size_t(3) * c->gk_nparts * MK * MK * sizeof(float)));
+  CU(cudaMalloc(&c->gk_partial2, size_t(3) * NCH * MK * MK * sizeof(double)));
+  CU(cudaMalloc(&c->gk_sum, size_t(3) * MK * MK * sizeof(double)));
   {
     int rc = make_maps(c);
     if (rc) { std::string keep = g_err; rltv_destroy(c); g_err = keep; return rc; }
   }
-  CU(cudaMalloc(&c->gk_partial2, size_t(3) * NCH * MK * MK * sizeof(double)));
   CU(cudaStreamSynchronize(c->stream));
   *out = c;
   return RLTV_OK;
+}
+
+int rltv_create(rltv_ctx** out, int32_t device, int32_t M, int32_t N, int32_t MK, void* stream) {
+  return rltv_create_band(out, device, M, N, MK, nullptr, stream);
 }
 
 int rltv_destroy(rltv_ctx* c) {
   if (!c) return RLTV_OK;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  float* f[] = {c->u, c->ut, c->gbuf, c->img, c->err, c->staging, c->psf, c->psf_caller, c->psf_hwc, c->gk_out,
+  for (auto& pb : c->peer_base) if (pb) cudaIpcCloseMemHandle(pb);
+  float* f[] = {c->u, c->ut, c->gbuf, c->img, c->err, c->staging, c->psf, c->psf_caller, c->psf_hwc,
                 c->gk_partial, c->rowmin, c->rowmax, c->mr_out};
   for (auto p : f) cudaFree(p);
-  double* d[] = {c->gk_partial2, c->wa, c->wb, c->rowacc, c->rowsum};
+  double* d[] = {c->gk_partial2, c->gk_sum, c->wa, c->wb, c->rowacc, c->rowsum};
   for (auto p : d) cudaFree(p);
-  cudaFree(c->Z); cudaFree(c->tw); cudaFree(c->st);
+  cudaFree(c->Z); cudaFree(c->tw); cudaFree(c->st); cudaFree(c->push_counter);
   if (c->h_st) cudaFreeHost(c->h_st);
   if (c->h_poll) cudaFreeHost(c->h_poll);
   for (auto& e : c->poll_ev) if (e) cudaEventDestroy(e);
@@ -499,22 +588,24 @@ int rltv_destroy(rltv_ctx* c) {
 
 void* rltv_stream(rltv_ctx* c) { return c ? reinterpret_cast<void*>(c->stream) : nullptr; }
 
-int rltv_upload(rltv_ctx* c, const float* image, size_t image_rs, const float* u, size_t u_rs, const float* psf) {
+int rltv_upload_band(rltv_ctx* c, const float* image, size_t image_rs, int32_t image_row0, int32_t n_image_rows,
+                     const float* u, size_t u_rs, const float* psf) {
   int rc = check_ctx(c);
   if (rc) return rc;
   const Geom& g = c->g;
-  if (image) {
+  if (image && n_image_rows > 0) {
     if (image_rs < size_t(g.N) * 12) return fail(RLTV_ERR_ARG, "image row stride smaller than a packed row");
-    CU(cudaMemcpy2DAsync(c->staging, size_t(g.N) * 12, image, image_rs, size_t(g.N) * 12, g.M, cudaMemcpyHostToDevice, c->stream));
-    k_hwc_to_planar<<<dim3((g.N * 3 + 255) / 256 > 64 ? 64 : (g.N * 3 + 255) / 256, g.M), 256, 0, c->stream>>>(
-        c->staging, size_t(g.N) * 3, g.M, g.N, c->img, g, g.P, g.P);
+    const int dst = image_row0 + g.P - g.row0;     // local row of the first provided image row
+    if (image_row0 < 0 || image_row0 + n_image_rows > g.M || dst < 0 || dst + n_image_rows > g.Hu)
+      return fail(RLTV_ERR_ARG, "image rows outside this band");
+    CU(cudaMemcpy2DAsync(c->staging, size_t(g.N) * 12, image, image_rs, size_t(g.N) * 12, n_image_rows, cudaMemcpyHostToDevice, c->stream));
+    k_hwc_to_planar<<<dim3(hwc_grid(g.N), n_image_rows), 256, 0, c->stream>>>(c->staging, size_t(g.N) * 3, n_image_rows, g.N, c->img, g, dst, g.P);
     c->launches++;
   }
   if (u) {
     if (u_rs < size_t(g.Wu) * 12) return fail(RLTV_ERR_ARG, "u row stride smaller than a packed row");
     CU(cudaMemcpy2DAsync(c->staging, size_t(g.Wu) * 12, u, u_rs, size_t(g.Wu) * 12, g.Hu, cudaMemcpyHostToDevice, c->stream));
-    k_hwc_to_planar<<<dim3((g.Wu * 3 + 255) / 256 > 64 ? 64 : (g.Wu * 3 + 255) / 256, g.Hu), 256, 0, c->stream>>>(
-        c->staging, size_t(g.Wu) * 3, g.Hu, g.Wu, c->u, g, 0, 0);
+    k_hwc_to_planar<<<dim3(hwc_grid(g.Wu), g.Hu), 256, 0, c->stream>>>(c->staging, size_t(g.Wu) * 3, g.Hu, g.Wu, c->u, g, 0, 0);
     c->launches++;
   }
   if (psf) {
@@ -530,16 +621,24 @@ int rltv_upload(rltv_ctx* c, const float* image, size_t image_rs, const float* u
   return RLTV_OK;
 }
 
-int rltv_download(rltv_ctx* c, float* u, size_t u_rs, float* psf_caller, float* psf_refined) {
+int rltv_upload(rltv_ctx* c, const float* image, size_t image_rs, const float* u, size_t u_rs, const float* psf) {
+  if (!c) return fail(RLTV_ERR_ARG, "null context");
+  if (c->banded) return fail(RLTV_ERR_STATE, "use rltv_upload_band on a row-band context");
+  return rltv_upload_band(c, image, image_rs, 0, image ? c->g.M : 0, u, u_rs, psf);
+}
+
+int rltv_download_rows(rltv_ctx* c, float* u, size_t u_rs, int32_t row0, int32_t nrows, float* psf_caller, float* psf_refined) {
   int rc = check_ctx(c);
   if (rc) return rc;
   const Geom& g = c->g;
-  if (u) {
+  if (u && nrows > 0) {
     if (u_rs < size_t(g.Wu) * 12) return fail(RLTV_ERR_ARG, "u row stride smaller than a packed row");
-    k_planar_to_hwc<<<dim3((g.Wu * 3 + 255) / 256 > 64 ? 64 : (g.Wu * 3 + 255) / 256, g.Hu), 256, 0, c->stream>>>(
-        c->u, g, 0, 0, g.Hu, g.Wu, c->staging, size_t(g.Wu) * 3);
+    const int l0 = row0 - g.row0;
+    if (l0 < 0 || l0 + nrows > g.Hu) return fail(RLTV_ERR_ARG, "rows not held by this band");
+    if (c->halo_pending) { if ((rc = launch_halo_wait(c)) != RLTV_OK) return rc; }
+    k_planar_to_hwc<<<dim3(hwc_grid(g.Wu), nrows), 256, 0, c->stream>>>(c->u, g, l0, 0, nrows, g.Wu, c->staging, size_t(g.Wu) * 3);
     c->launches++;
-    CU(cudaMemcpy2DAsync(u, u_rs, c->staging, size_t(g.Wu) * 12, size_t(g.Wu) * 12, g.Hu, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpy2DAsync(u, u_rs, c->staging, size_t(g.Wu) * 12, size_t(g.Wu) * 12, nrows, cudaMemcpyDeviceToHost, c->stream));
   }
   const int KK2 = g.K * g.K;
   float* dsts[2] = {psf_caller, psf_refined};
@@ -554,6 +653,11 @@ int rltv_download(rltv_ctx* c, float* u, size_t u_rs, float* psf_caller, float* 
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(c->stream));
   return RLTV_OK;
+}
+
+int rltv_download(rltv_ctx* c, float* u, size_t u_rs, float* psf_caller, float* psf_refined) {
+  if (!c) return fail(RLTV_ERR_ARG, "null context");
+  return rltv_download_rows(c, u, u_rs, c->row_lo, u ? c->g.Hu : 0, psf_caller, psf_refined);
 }
 
 int rltv_begin(rltv_ctx* c, const rltv_params_t* p) {
@@ -574,14 +678,40 @@ int rltv_begin(rltv_ctx* c, const rltv_params_t* p) {
   return RLTV_OK;
 }
 
+int rltv_enqueue_phase(rltv_ctx* c, int32_t phase) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  if (!c->begun) return fail(RLTV_ERR_STATE, "rltv_begin must precede rltv_enqueue_phase");
+  return enqueue_phase(c, phase);
+}
+
 int rltv_enqueue_outer(rltv_ctx* c, int32_t n_outer) {
   int rc = check_ctx(c);
   if (rc) return rc;
   if (!c->begun) return fail(RLTV_ERR_STATE, "rltv_begin must precede rltv_enqueue_outer");
+  if (c->banded) return fail(RLTV_ERR_STATE, "row bands are stepped phase by phase (rltv_enqueue_phase)");
   for (int i = 0; i < n_outer; ++i) {
     if ((rc = enqueue_outer(c)) != RLTV_OK) return rc;
     c->outer_enqueued++;
   }
+  return RLTV_OK;
+}
+
+int rltv_poll_record(rltv_ctx* c, int32_t it) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  const int slot = it & 3;
+  CU(cudaMemcpyAsync(c->h_poll + 2 * slot, c->st, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaEventRecord(c->poll_ev[slot], c->stream));
+  return RLTV_OK;
+}
+
+int rltv_poll_wait(rltv_ctx* c, int32_t it, int32_t* stop) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  const int slot = it & 3;
+  CU(cudaEventSynchronize(c->poll_ev[slot]));
+  if (stop) *stop = c->h_poll[2 * slot];
   return RLTV_OK;
 }
 
@@ -600,20 +730,19 @@ int rltv_finish(rltv_ctx* c, rltv_stats_t* stats) {
 }
 
 int rltv_solve(rltv_ctx* c, const rltv_params_t* p, rltv_stats_t* stats) {
+  if (c && c->banded) return fail(RLTV_ERR_STATE, "row bands are driven by the distributed host loop");
   int rc = rltv_begin(c, p);
   if (rc) return rc;
   // Host runs at most two outer iterations ahead of the device-side stop flag.
   for (int it = 0; it < p->iterations; ++it) {
     if (it >= 2) {
-      const int slot = (it - 2) & 3;
-      CU(cudaEventSynchronize(c->poll_ev[slot]));
-      if (c->h_poll[2 * slot]) break;
+      int stop = 0;
+      if ((rc = rltv_poll_wait(c, it - 2, &stop)) != RLTV_OK) return rc;
+      if (stop) break;
     }
     if ((rc = enqueue_outer(c)) != RLTV_OK) return rc;
     c->outer_enqueued++;
-    const int slot = it & 3;
-    CU(cudaMemcpyAsync(c->h_poll + 2 * slot, c->st, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaEventRecord(c->poll_ev[slot], c->stream));
+    if ((rc = rltv_poll_record(c, it)) != RLTV_OK) return rc;
   }
   return rltv_finish(c, stats);
 }
@@ -635,11 +764,72 @@ int rltv_profile_get(rltv_ctx* c, const char* family, float* total_ms, int32_t* 
   return fail(RLTV_ERR_ARG, "unknown kernel family");
 }
 
+// ---- row bands -----------------------------------------------------------------------------------------
+int rltv_ipc_export(rltv_ctx* c, void* handle64) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, c->u));
+  std::memcpy(handle64, &h, 64);
+  return RLTV_OK;
+}
+
+int rltv_ipc_attach(rltv_ctx* c, int32_t side, const void* handle64, int32_t peer_row_lo, int32_t peer_row_hi) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  if (side < 0 || side > 1 || !handle64) return fail(RLTV_ERR_ARG, "bad side/handle");
+  const int P2 = 2 * c->g.P;
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle64, 64);
+  void* base = nullptr;
+  CU(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+  c->peer_base[side] = base;
+  const size_t peer_plane = size_t(peer_row_hi - peer_row_lo) * c->g.pitch;
+  const size_t peer_flag_off = (3 * peer_plane * sizeof(float) + 255) & ~size_t(255);
+  HaloSide& s = c->side[side];
+  s.peer_u = reinterpret_cast<float*>(base);
+  s.peer_plane = peer_plane;
+  s.nrows = P2;
+  if (side == 0) {
+    // band above: its bottom halo = frame rows [own_lo, own_lo + 2P) = my first owned rows; I am ITS lower neighbour
+    s.src_row = c->own_lo - c->row_lo;
+    s.dst_row = c->own_lo - peer_row_lo;
+    s.peer_flag = reinterpret_cast<int*>(reinterpret_cast<char*>(base) + peer_flag_off) + 1;
+  } else {
+    // band below: its top halo = frame rows [own_hi - 2P, own_hi) = my last owned rows; I am ITS upper neighbour
+    s.src_row = c->own_hi - P2 - c->row_lo;
+    s.dst_row = c->own_hi - P2 - peer_row_lo;
+    s.peer_flag = reinterpret_cast<int*>(reinterpret_cast<char*>(base) + peer_flag_off) + 0;
+  }
+  if (s.src_row < c->g.own0 || s.src_row + s.nrows > c->g.own1 || s.dst_row < 0 || s.dst_row + s.nrows > peer_row_hi - peer_row_lo)
+    return fail(RLTV_ERR_ARG, "halo rows do not fit: every band must own at least 2*(MK/2) rows");
+  return RLTV_OK;
+}
+
+int rltv_set_whiteness_owner(rltv_ctx* c, int32_t owner) {
+  if (!c) return fail(RLTV_ERR_ARG, "null context");
+  c->white_owner = owner != 0;
+  return RLTV_OK;
+}
+
+void* rltv_device_ptr(rltv_ctx* c, const char* name, size_t* nbytes) {
+  if (!c || !name) return nullptr;
+  size_t n = 0;
+  void* p = nullptr;
+  if (!std::strcmp(name, "step_max")) { p = c->st->max_u; n = 6 * sizeof(int); }
+  else if (!std::strcmp(name, "gk_sum")) { p = c->gk_sum; n = size_t(3) * c->g.K * c->g.K * sizeof(double); }
+  else if (!std::strcmp(name, "stop")) { p = &c->st->stop; n = sizeof(int); }
+  if (nbytes) *nbytes = n;
+  return p;
+}
+
 // ---- stage-level entry points ------------------------------------------------------------------------
 int rltv_stage_residual(rltv_ctx* c, float* err_out) {
   int rc = check_ctx(c);
   if (rc) return rc;
   if (!c->uploaded) return fail(RLTV_ERR_STATE, "upload first");
+  if (c->banded) return fail(RLTV_ERR_STATE, "stage entry points need a whole-frame context");
   const Geom& g = c->g;
   CU(cudaMemsetAsync(c->st, 0, sizeof(State), c->stream));
   if ((rc = launch_conv_fwd(c)) != RLTV_OK) return rc;
@@ -656,6 +846,7 @@ int rltv_stage_adjoint(rltv_ctx* c, float* g_out) {
   int rc = check_ctx(c);
   if (rc) return rc;
   if (!c->uploaded) return fail(RLTV_ERR_STATE, "upload first");
+  if (c->banded) return fail(RLTV_ERR_STATE, "stage entry points need a whole-frame context");
   const Geom& g = c->g;
   CU(cudaMemcpyAsync(c->ut, c->u, 3 * g.plane * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
   if ((rc = launch_conv_adj(c, 1.0f)) != RLTV_OK) return rc;
@@ -672,20 +863,18 @@ int rltv_stage_gradk(rltv_ctx* c, float* gk_out) {
   int rc = check_ctx(c);
   if (rc) return rc;
   if (!c->uploaded) return fail(RLTV_ERR_STATE, "upload first");
+  if (c->banded) return fail(RLTV_ERR_STATE, "stage entry points need a whole-frame context");
   const int K = c->g.K, KK2 = K * K;
   if ((rc = launch_gradk(c)) != RLTV_OK) return rc;
-  std::vector<double> p2(size_t(3) * NCH * KK2);
-  CU(cudaMemcpyAsync(p2.data(), c->gk_partial2, p2.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  std::vector<double> s(size_t(3) * KK2);
+  CU(cudaMemcpyAsync(s.data(), c->gk_sum, s.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaGetLastError());
-  // final fixed-order sum + the K-1-q index flip, exactly as k_psf_update does it
+  // the K-1-q index flip, exactly as k_psf_update does it
   for (int ch = 0; ch < 3; ++ch)
     for (int q = 0; q < KK2; ++q) {
       const int qy = q / K, qx = q % K;
-      const int o = (K - 1 - qy) * K + (K - 1 - qx);
-      double s = 0.0;
-      for (int k = 0; k < NCH; ++k) s += p2[(size_t(ch) * NCH + k) * KK2 + o];
-      gk_out[q * 3 + ch] = float(s);
+      gk_out[q * 3 + ch] = float(s[size_t(ch) * KK2 + (K - 1 - qy) * K + (K - 1 - qx)]);
     }
   return RLTV_OK;
 }
@@ -694,6 +883,7 @@ int rltv_stage_whiteness(rltv_ctx* c, int32_t top, int32_t bottom, int32_t left,
   int rc = check_ctx(c);
   if (rc) return rc;
   if (!c->uploaded) return fail(RLTV_ERR_STATE, "upload first");
+  if (c->banded) return fail(RLTV_ERR_STATE, "stage entry points need a whole-frame context");
   if ((rc = setup_whiteness(c, top, bottom, left, right)) != RLTV_OK) return rc;
   if ((rc = launch_whiteness(c, 0)) != RLTV_OK) return rc;
   float v = 0.f;

@@ -15,11 +15,14 @@
 namespace rltv {
 
 struct Geom {
-  int M, N;      // image rows / cols
+  int M, N;      // image rows / cols of the WHOLE frame
   int K, P;      // PSF size, pad = K/2
-  int Hu, Wu;    // M + K - 1, N + K - 1
+  int Hu, Wu;    // rows held by this context (whole frame: M + K - 1; row band: owned rows + halos), N + K - 1
   int pitch;     // floats per row of every plane
   size_t plane;  // floats per plane (Hu * pitch)
+  // Row-band sharding (one band per GPU): local row Y is row (row0 + Y) of the frame's u-geometry; rows
+  // [own0, own1) are owned (updated, counted in reductions), the rest are halo copies of the neighbours' rows.
+  int row0, own0, own1;
 };
 
 // Device-resident solver state: everything the host would otherwise have to read back between kernels.
@@ -28,8 +31,9 @@ struct State {
   int it;                  // outer iterations executed (pyx:456,:656)
   int blind_steps;         // PSF steps taken (for the `correlation` caller-array quirk, pyx:581-585)
   float M_r, M_r_prev;     // pyx:624,:638
-  unsigned max_u[3];       // order-preserving uint encoding of max(u_c)          (pyx:524)
-  unsigned max_G[3];       //                                  max|gradu_c|       (pyx:524)
+  int max_u[3];            // order-preserving int encoding of max(u_c)           (pyx:524)
+  int max_G[3];            //                                 max|gradu_c|        (pyx:524)
+                           // (6 contiguous int32: one MAX all-reduce across row bands)
   float dt[3];             // last image step sizes
   float dtpsf;             // last PSF step size (pyx:574)
   double win_sum;          // whiteness window: sum, min, max of the residual (pyx:627-629)
@@ -39,14 +43,13 @@ struct State {
   float hist[4096];
 };
 
-// Monotone float -> uint map so that atomicMax on the encoding is a float max (any sign).
-__device__ __forceinline__ unsigned f2ord(float f) {
-  unsigned b = __float_as_uint(f);
-  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+// Monotone float -> signed int map: atomicMax (and an int32 MAX all-reduce) on the encoding is a float max.
+__device__ __forceinline__ int f2ord(float f) {
+  const int b = __float_as_int(f);
+  return b >= 0 ? b : (b ^ 0x7fffffff);
 }
-__device__ __forceinline__ float ord2f(unsigned o) {
-  return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
-}
+__device__ __forceinline__ float ord2f(int o) { return __int_as_float(o >= 0 ? o : (o ^ 0x7fffffff)); }
+constexpr int ORD_LOWEST = int(0x80000000u);
 
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll

@@ -15,11 +15,11 @@ k_update(Geom g, State* __restrict__ st, float* __restrict__ u, const float* __r
          const float* __restrict__ gbuf, const float* __restrict__ img, float step, float lambd, int blind) {
   if (st->stop) return;
   const int c = blockIdx.z;
-  const int Y = blockIdx.y;
+  const int Y = g.own0 + blockIdx.y;          // only owned rows are updated; halo rows arrive from the neighbours
   const int X = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
   // dt = step_factor * (amax(u_c) + 0) / (amax|gradu_c| + 1e-15), float32 like the reference (pyx:524)
   const float dt = step * ord2f(st->max_u[c]) / (ord2f(st->max_G[c]) + 1e-15f);
-  if (X == 0 && Y == 0) st->dt[c] = dt;
+  if (X == 0 && blockIdx.y == 0) st->dt[c] = dt;
   if (X >= g.Wu) return;
   const size_t off = size_t(c) * g.plane + size_t(Y) * g.pitch + X;
   const float4 uv = *reinterpret_cast<const float4*>(u + off);
@@ -28,7 +28,8 @@ k_update(Geom g, State* __restrict__ st, float* __restrict__ u, const float* __r
   const float4 iv = *reinterpret_cast<const float4*>(img + off);
   const float uu[4] = {uv.x, uv.y, uv.z, uv.w}, tt[4] = {tv.x, tv.y, tv.z, tv.w};
   const float gg[4] = {gv.x, gv.y, gv.z, gv.w}, ii[4] = {iv.x, iv.y, iv.z, iv.w};
-  const bool rowin = (Y >= g.P) && (Y < g.P + g.M);
+  const int gy = g.row0 + Y;
+  const bool rowin = (gy >= g.P) && (gy < g.P + g.M);
   float o[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -47,14 +48,13 @@ k_update(Geom g, State* __restrict__ st, float* __restrict__ u, const float* __r
 
 // ------------------------------------------------------------------------------------------------
 // K5: PSF step (pyx:574-589).  One block.  psf / psf_caller layout: planar [3][K*K].
-//   gk[q] = gk'[K-1-q] (sum of the NCH double partials); dtpsf = step/K * amax(psf) / (amax|gk| + 1e-15);
+//   gk[q] = gk'[K-1-q] (gk' = gk_sum, the double-precision sum over tiles -- and over row bands); dtpsf = step/K * amax(psf) / (amax|gk| + 1e-15);
 //   psf -= dtpsf * gk ; (correlation: every channel = channel mean) ; clip < 0 ; divide by channel sum.
 // `psf_caller` reproduces what the CALLER's array holds in the reference: it tracks psf, except that with
 // `correlation` it freezes after the first un-normalised step (pyx:581 writes in place, pyx:585 rebinds).
 // ------------------------------------------------------------------------------------------------
-template <int NCH>
 __global__ void __launch_bounds__(256)
-k_psf_update(State* __restrict__ st, const double* __restrict__ partial2, int K, float step, int correlation,
+k_psf_update(State* __restrict__ st, const double* __restrict__ gk_sum, int K, float step, int correlation,
              float* __restrict__ psf, float* __restrict__ psf_caller) {
   if (st->stop) return;
   extern __shared__ float sm[];
@@ -70,9 +70,7 @@ k_psf_update(State* __restrict__ st, const double* __restrict__ partial2, int K,
     const int c = i / KK2, q = i - c * KK2;
     const int qy = q / K, qx = q - qy * K;
     const int o = (K - 1 - qy) * K + (K - 1 - qx);
-    double s = 0.0;
-    for (int ch = 0; ch < NCH; ++ch) s += partial2[(size_t(c) * NCH + ch) * KK2 + o];
-    const float v = float(s);
+    const float v = float(gk_sum[c * KK2 + o]);
     gk[i] = v;
     const float p = psf[i];
     pk[i] = p;

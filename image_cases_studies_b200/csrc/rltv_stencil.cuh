@@ -133,13 +133,14 @@ __device__ __forceinline__ void stencil_core(const float* __restrict__ tile, con
 //     tm_in = u (box SP x SROWS), tm_e0 = image (box TW x TH)
 // K2 (ADJ = true): g = full_conv(err, rot180 psf); max(u_c), max|lambda*g + (u-ut)/2|   pyx:490-491, :519, :524
 //     tm_in = err, tm_e0 = u, tm_e1 = ut
+// Output rows [ybeg, yend) of the local band (whole frame: all rows; row band: the rows this band needs).
 // Tiles are numbered x-fastest inside a channel; CTA b processes tiles b, b+grid, b+2*grid, ...
 // ------------------------------------------------------------------------------------------------
 template <int K, bool ADJ>
 __global__ void __launch_bounds__(ConvCfg<K>::THREADS, 2)
 k_conv(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_e0,
        const __grid_constant__ CUtensorMap tm_e1, Geom g, State* __restrict__ st, const float* __restrict__ psf,
-       float lambd, float* __restrict__ out, int ntx, int nty) {
+       float lambd, float* __restrict__ out, int ntx, int nty, int ybeg, int yend) {
   using C = ConvCfg<K>;
   if (st->stop) return;
   extern __shared__ unsigned char smem_raw[];
@@ -156,8 +157,8 @@ k_conv(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtens
 
   if (!ADJ && blockIdx.x == 0 && tid < 3) {
     // first kernel of an inner step: reset the step-size reductions the adjoint kernel accumulates into
-    st->max_u[tid] = 0u;
-    st->max_G[tid] = 0u;
+    st->max_u[tid] = ORD_LOWEST;
+    st->max_G[tid] = 0;
   }
   if (tid == 0) {
     mbar_init(&bars[0], 1);
@@ -174,14 +175,14 @@ k_conv(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtens
     const int c = t / tiles_per_c, r = t - c * tiles_per_c;
     const int by = r / ntx, bx = r - by * ntx;
     mbar_arrive_expect_tx(&bars[s], C::IN_BYTES);
-    tma_load_3d(smem + s * C::IN_STRIDE, &tm_in, bx * C::TW - C::P4, by * C::TH - C::P, c, &bars[s]);
+    tma_load_3d(smem + s * C::IN_STRIDE, &tm_in, bx * C::TW - C::P4, ybeg + by * C::TH - C::P, c, &bars[s]);
   };
   auto issue_epi = [&](int t) {
     const int c = t / tiles_per_c, r = t - c * tiles_per_c;
     const int by = r / ntx, bx = r - by * ntx;
     mbar_arrive_expect_tx(&bars[2], (ADJ ? 2 : 1) * C::EPI_BYTES);
-    tma_load_3d(e0, &tm_e0, bx * C::TW, by * C::TH, c, &bars[2]);
-    if (ADJ) tma_load_3d(e1, &tm_e1, bx * C::TW, by * C::TH, c, &bars[2]);
+    tma_load_3d(e0, &tm_e0, bx * C::TW, ybeg + by * C::TH, c, &bars[2]);
+    if (ADJ) tma_load_3d(e1, &tm_e1, bx * C::TW, ybeg + by * C::TH, c, &bars[2]);
   };
 
   int t = blockIdx.x;
@@ -218,13 +219,14 @@ k_conv(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtens
       float* op = out + size_t(c) * g.plane;
 #pragma unroll
       for (int j = 0; j < C::R; ++j) {
-        const int Y = by * C::TH + warp * C::R + j;
-        if (Y >= g.Hu) break;
+        const int Y = ybeg + by * C::TH + warp * C::R + j;
+        if (Y >= yend) break;
         const float4 a = *reinterpret_cast<const float4*>(e0 + (warp * C::R + j) * C::TW + 4 * lane);
         const float av[4] = {a.x, a.y, a.z, a.w};
         float o[4];
         if (!ADJ) {
-          const bool rowin = (Y >= C::P) && (Y < C::P + g.M);
+          const int gy = g.row0 + Y;
+          const bool rowin = (gy >= C::P) && (gy < C::P + g.M);
 #pragma unroll
           for (int i = 0; i < 4; ++i)
             o[i] = (rowin && (X + i) >= C::P && (X + i) < C::P + g.N) ? acc[j][i] - av[i] : 0.f;
@@ -235,7 +237,7 @@ k_conv(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtens
           for (int i = 0; i < 4; ++i) {
             const bool in = (X + i) < g.Wu;
             o[i] = in ? acc[j][i] : 0.f;
-            if (in) {
+            if (in && Y >= g.own0 && Y < g.own1) {   // statistics over owned rows only (row bands)
               const float G = fmaf(lambd, acc[j][i], 0.5f * (av[i] - bv[i]));   // pyx:519
               mu = fmaxf(mu, av[i]);
               mG = fmaxf(mG, fabsf(G));
@@ -387,7 +389,9 @@ k_gradk(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtens
     const int c = item / C::NCHUNK, dyb = (item - c * C::NCHUNK) * C::DYB;
     const int by = tl / ntx, bx = tl - by * ntx;
     mbar_arrive_expect_tx(&bars[s], C::U_BYTES + C::E_BYTES);
-    tma_load_3d(smem + s * C::STAGE, &tm_u, bx * C::TW - C::P4, by * C::TH - C::P + dyb, c, &bars[s]);
+    // tm_e covers the OWNED rows only (row 0 of that map = local row own0): rows outside arrive as zeros,
+    // so halo rows never contribute to the PSF gradient
+    tma_load_3d(smem + s * C::STAGE, &tm_u, bx * C::TW - C::P4, g.own0 + by * C::TH - C::P + dyb, c, &bars[s]);
     tma_load_3d(smem + s * C::STAGE + C::U_STRIDE, &tm_e, bx * C::TW, by * C::TH, c, &bars[s]);
   };
 
@@ -467,6 +471,19 @@ __global__ void k_gradk_reduce(const State* __restrict__ st, const float* __rest
     double s = 0.0;
     for (int t = t0; t < t1; ++t) s += double(partial[(size_t(c) * nparts + t) * KK2 + o]);
     partial2[(size_t(c) * NCH + chunk) * KK2 + o] = s;
+  }
+}
+
+// Stage 2: gk_sum[c][o] = sum over the NCH chunks, fixed order (double).  Row bands all-reduce this buffer.
+template <int NCH>
+__global__ void k_gradk_final(const State* __restrict__ st, const double* __restrict__ partial2, int KK2,
+                              double* __restrict__ gk_sum) {
+  if (st->stop) return;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 3 * KK2; i += gridDim.x * blockDim.x) {
+    const int c = i / KK2, o = i - c * KK2;
+    double s = 0.0;
+    for (int ch = 0; ch < NCH; ++ch) s += partial2[(size_t(c) * NCH + ch) * KK2 + o];
+    gk_sum[i] = s;
   }
 }
 

@@ -26,7 +26,7 @@ k_win_rows(Geom g, const State* __restrict__ st, const float* __restrict__ err, 
            double* __restrict__ rowsum, float* __restrict__ rowmin, float* __restrict__ rowmax) {
   if (st->stop) return;
   const int y = blockIdx.x, c = blockIdx.y;
-  const float* row = err + size_t(c) * g.plane + size_t(wg.top + g.P + y) * g.pitch + (wg.left + g.P);
+  const float* row = err + size_t(c) * g.plane + size_t(wg.top + g.P - g.row0 + y) * g.pitch + (wg.left + g.P);
   double s = 0.0;
   float mn = INFINITY, mx = -INFINITY;
   for (int x = threadIdx.x; x < wg.w; x += blockDim.x) {
@@ -102,7 +102,7 @@ __global__ void k_white_rows_fwd(Geom g, const State* __restrict__ st, const flo
   const double mean = st->win_sum / (3.0 * wg.h * wg.w);
   const double dev = fmax(double(st->win_max) - mean, mean - double(st->win_min));
   const double scale = 1.0 / dev;
-  const float* row = err + size_t(c) * g.plane + size_t(wg.top + g.P + y) * g.pitch + (wg.left + g.P);
+  const float* row = err + size_t(c) * g.plane + size_t(wg.top + g.P - g.row0 + y) * g.pitch + (wg.left + g.P);
   for (int i = threadIdx.x; i < L; i += blockDim.x) {
     const int r = __brev(unsigned(i)) >> (32 - wg.log2L);
     sd[r] = make_double2(i < wg.w ? (double(row[i]) - mean) * scale : 0.0, 0.0);
@@ -180,10 +180,16 @@ __global__ void k_white_rows_inv(const State* __restrict__ st, WhiteGeom wg, con
 }
 
 // S6: one thread: M_r, stop rule (pyx:623-656).  advance == 0: only report (stage-level test entry point).
+// owner == 0 (row band that does not hold the whiteness window): only the iteration counter advances; the
+// stop flag arrives by an int32 MAX all-reduce from the owning band.
 __global__ void k_outer_finalize(State* __restrict__ st, WhiteGeom wg, const double* __restrict__ rowacc,
-                                 int blind, float tau, int advance, float* __restrict__ out) {
+                                 int blind, float tau, int advance, int owner, float* __restrict__ out) {
   if (st->stop) return;
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (!owner) {
+    if (advance) st->it = st->it + 1;
+    return;
+  }
   double t = 0.0;
   for (int i = 0; i < 3 * wg.h; ++i) t += rowacc[i];
   const float M_r = float(t / (3.0 * double(wg.h) * double(wg.w)));   // np.mean(test), pyx:638

@@ -12,7 +12,7 @@ import numpy as np
 
 from . import _native as nat
 
-FAMILIES = ("conv_fwd", "conv_adj", "update", "gradk", "psf", "stats", "copy")
+FAMILIES = ("conv_fwd", "conv_adj", "update", "gradk", "psf", "stats", "copy", "halo")
 
 
 def default_device() -> int:

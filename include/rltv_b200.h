@@ -31,7 +31,7 @@ extern "C" {
 
 #define RLTV_ABI_VERSION 1
 #define RLTV_INNER_ITER 5       /* pyx:375 */
-#define RLTV_MAX_MK 63          /* direct stencils are instantiated for odd MK in [3, 63] */
+#define RLTV_MAX_MK 31          /* direct stencils are instantiated for odd MK in [3, 31] */
 #define RLTV_MAX_HISTORY 4096   /* outer iterations whose M_r is kept in rltv_stats_t.M_r_history */
 
 typedef enum {
@@ -90,8 +90,7 @@ int rltv_normalize_kernel(float* kern, int32_t MK, int32_t device);
 /* ---- persistent context (device-resident state; what bench.py times and the multi-GPU driver uses) -- */
 
 /* `stream` is a cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream) or NULL for a private one.
- * The context owns planar device copies of image/u/ut/g/err for an (M,N,MK) problem.
- * Row-band sharding: the context may hold only rows [row0, row0+rows) of a frame of `M_total` rows. */
+ * The context owns planar device copies of image/u/ut/g/err for an (M,N,MK) problem. */
 int rltv_create(rltv_ctx** ctx, int32_t device, int32_t M, int32_t N, int32_t MK, void* stream);
 int rltv_destroy(rltv_ctx* ctx);
 int rltv_upload(rltv_ctx* ctx, const float* image, size_t image_row_stride_bytes,
@@ -110,6 +109,43 @@ void* rltv_stream(rltv_ctx* ctx);
  * rltv_begin, for bench.py's roofline.  names: "conv_fwd","conv_adj","update","gradk","psf","stats","copy". */
 int rltv_profile_enable(rltv_ctx* ctx, int32_t on);
 int rltv_profile_get(rltv_ctx* ctx, const char* family, float* total_ms, int32_t* launches);
+
+/* ---- row-band sharding: one context per GPU holds a band of rows of ONE frame ----------- */
+/* Rows are rows of the padded estimate u (0 .. M+MK-2).  A band HOLDS rows [row_lo, row_hi) and OWNS
+ * [own_lo, own_hi) of them; the rest are halos of width 2*(MK/2) copied from the neighbouring bands.  The host
+ * side (image_cases_studies_b200/distributed.py) plans the bands, exchanges IPC handles and issues the
+ * NCCL all-reduces between phases; this library does the halo exchange itself with peer stores over NVLink. */
+typedef struct {
+  int32_t row_lo, row_hi;   /* rows held */
+  int32_t own_lo, own_hi;   /* rows owned (updated here, counted in reductions) */
+} rltv_band_t;
+
+int rltv_create_band(rltv_ctx** ctx, int32_t device, int32_t M, int32_t N, int32_t MK, const rltv_band_t* band,
+                     void* stream);
+/* image_rows: `n_image_rows` rows of the blurry image starting at image row `image_row0`; u_rows: rows
+ * row_lo .. row_hi-1 of u. */
+int rltv_upload_band(rltv_ctx* ctx, const float* image_rows, size_t image_row_stride_bytes, int32_t image_row0,
+                     int32_t n_image_rows, const float* u_rows, size_t u_row_stride_bytes, const float* psf);
+/* copies u rows [row0, row0+nrows) (frame coordinates, must be held by this band) to the host */
+int rltv_download_rows(rltv_ctx* ctx, float* u_rows, size_t u_row_stride_bytes, int32_t row0, int32_t nrows,
+                       float* psf_caller, float* psf_refined);
+/* CUDA IPC: `handle` is a 64-byte cudaIpcMemHandle_t of this band's u allocation (which also carries the
+ * halo flags).  side 0 = the band above (previous rank), 1 = the band below. */
+int rltv_ipc_export(rltv_ctx* ctx, void* handle64);
+int rltv_ipc_attach(rltv_ctx* ctx, int32_t side, const void* handle64, int32_t peer_row_lo, int32_t peer_row_hi);
+/* exactly one band evaluates the whiteness statistic / stop rule (the one holding the window rows) */
+int rltv_set_whiteness_owner(rltv_ctx* ctx, int32_t owner);
+/* one outer iteration = BEGIN, 5 x (GRAD, [all-reduce MAX step_max], UPDATE, blind: PSF_GRAD,
+ * [all-reduce SUM gk_sum], PSF_STEP), END, [all-reduce MAX stop] */
+enum { RLTV_PH_OUTER_BEGIN = 0, RLTV_PH_GRAD = 1, RLTV_PH_UPDATE = 2, RLTV_PH_PSF_GRAD = 3, RLTV_PH_PSF_STEP = 4,
+       RLTV_PH_OUTER_END = 5 };
+int rltv_enqueue_phase(rltv_ctx* ctx, int32_t phase);
+/* device pointers the host all-reduces in place: "step_max" (6 x int32), "gk_sum" (3*MK*MK x double),
+ * "stop" (1 x int32) */
+void* rltv_device_ptr(rltv_ctx* ctx, const char* name, size_t* nbytes);
+/* deterministic host-side stop polling: record after outer iteration `it`, wait for iteration `it` */
+int rltv_poll_record(rltv_ctx* ctx, int32_t it);
+int rltv_poll_wait(rltv_ctx* ctx, int32_t it, int32_t* stop);
 
 /* ---- stage-level entry points (parity tests drive each kernel against the oracle) ------------------ */
 /* out[M][N][3] = valid-conv(u, psf) - image   (pyx:477-488) */

@@ -1,0 +1,67 @@
+"""torchrun worker for the multi-GPU parity test: row-band sharded solve (NCCL + NVLink peer stores) against the
+single-GPU solve of the same frame.  Launched by tests/test_gpu_bands.py; every rank exits non-zero on failure."""
+import json
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from helpers import psf_l1, rel_l2
+    from image_cases_studies_b200 import distributed, synthetic
+    from image_cases_studies_b200.lib import deconvolution as dc
+
+    report = {}
+    cases = [("c2_blind_2mp_k9", 0.35, 4, False), ("c1_nonblind_512_g5", 1.0, 3, False),
+             ("c3_blind_24mp_k15", 0.12, 2, True)]
+    for name, scale, iters, corr in cases:
+        c = synthetic.make_case(name, seed=11, scale=scale, iterations=iters)
+        M, N = c.shape
+        u_d, psf_d = c.u0.copy(), c.psf0.copy()
+        out_d = distributed.richardson_lucy_MM(c.image, u_d, psf_d, *c.window, c.tau, M, N, 3, c.MK, c.iterations,
+                                               c.step_factor, c.lambd, blind=c.blind, correlation=corr)
+        st_d = distributed.richardson_lucy_MM.last_stats
+        ok = True
+        if rank == 0:
+            u_s, psf_s = c.u0.copy(), c.psf0.copy()
+            out_s = dc.richardson_lucy_MM(c.image, u_s, psf_s, *c.window, c.tau, M, N, 3, c.MK, c.iterations,
+                                          c.step_factor, c.lambd, blind=c.blind, correlation=corr)
+            st_s = dc.last_stats
+            r = dict(rel_u=rel_l2(u_d, u_s), psf=psf_l1(psf_d, psf_s), its=(st_d["iterations"], st_s["iterations"]),
+                     mr=float(np.max(np.abs(np.array(st_d["M_r_history"]) - np.array(st_s["M_r_history"])) /
+                                     np.array(st_s["M_r_history"]))) if st_s["M_r_history"] else 0.0,
+                     moved=rel_l2(u_s, c.u0))
+            report[name] = r
+            # identical algorithm, different summation order of the PSF gradient only
+            ok = (r["rel_u"] <= 1e-6 and r["psf"] <= 1e-6 and r["its"][0] == r["its"][1] and r["mr"] <= 1e-5
+                  and r["moved"] > 1e-7)
+            print(name, M, N, c.MK, r, "OK" if ok else "FAIL", flush=True)
+        flag = torch.tensor([0 if ok else 1], device=f"cuda:{local}")
+        dist.all_reduce(flag)
+        # every rank must hold the same full result
+        chk = torch.tensor([float(u_d.astype(np.float64).sum()), float(psf_d.astype(np.float64).sum())], device=f"cuda:{local}", dtype=torch.float64)
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        if flag.item() or not torch.equal(lo, hi):
+            print("rank", rank, "mismatch", flag.item(), lo.tolist(), hi.tolist(), flush=True)
+            dist.destroy_process_group()
+            sys.exit(1)
+    if rank == 0 and len(sys.argv) > 1:
+        Path(sys.argv[1]).write_text(json.dumps(report))
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
