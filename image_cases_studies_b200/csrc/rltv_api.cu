@@ -24,6 +24,7 @@
 #include "rltv_common.cuh"
 #include "rltv_elementwise.cuh"
 #include "rltv_stencil.cuh"
+#include "rltv_tv.cuh"
 #include "rltv_whiteness.cuh"
 
 using namespace rltv;
@@ -891,6 +892,39 @@ int rltv_stage_whiteness(rltv_ctx* c, int32_t top, int32_t bottom, int32_t left,
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaGetLastError());
   if (M_r) *M_r = v;
+  return RLTV_OK;
+}
+
+// TV(u, out, ..., epsilon, order, norm, div) of pyx:137-239 on the estimate currently on the device.
+// `out` goes to the g buffer, `div` to the err buffer (both are scratch between solves).
+int rltv_stage_tv(rltv_ctx* c, int32_t order, int32_t norm, float epsilon, float* out_hwc, float* div_hwc, float* ms) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  if (!c->uploaded) return fail(RLTV_ERR_STATE, "upload first");
+  if (c->banded) return fail(RLTV_ERR_STATE, "stage entry points need a whole-frame context");
+  if ((order != 1 && order != 2) || (norm != 1 && norm != 2)) return fail(RLTV_ERR_ARG, "order and norm must be 1 or 2");
+  const Geom& g = c->g;
+  dim3 grid((g.pitch / 4 + 255) / 256, g.Hu, 3);
+  CU(cudaEventRecord(c->ev0, c->stream));
+  if (order == 2 && norm == 1) k_tv<2, 1><<<grid, 256, 0, c->stream>>>(g, c->u, epsilon, c->gbuf, c->err);
+  if (order == 2 && norm == 2) k_tv<2, 2><<<grid, 256, 0, c->stream>>>(g, c->u, epsilon, c->gbuf, c->err);
+  if (order == 1 && norm == 1) k_tv<1, 1><<<grid, 256, 0, c->stream>>>(g, c->u, epsilon, c->gbuf, c->err);
+  if (order == 1 && norm == 2) k_tv<1, 2><<<grid, 256, 0, c->stream>>>(g, c->u, epsilon, c->gbuf, c->err);
+  CU(cudaEventRecord(c->ev1, c->stream));
+  float* srcs[2] = {c->gbuf, c->err};
+  float* dsts[2] = {out_hwc, div_hwc};
+  for (int i = 0; i < 2; ++i) {
+    if (!dsts[i]) continue;
+    k_planar_to_hwc<<<dim3(hwc_grid(g.Wu), g.Hu), 256, 0, c->stream>>>(srcs[i], g, 0, 0, g.Hu, g.Wu, c->staging, size_t(g.Wu) * 3);
+    CU(cudaMemcpyAsync(dsts[i], c->staging, size_t(g.Hu) * g.Wu * 12, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  if (ms) cudaEventElapsedTime(ms, c->ev0, c->ev1);
+  // the residual buffer was used as scratch: restore its zero ring for the next solve
+  CU(cudaMemsetAsync(c->err, 0, 3 * g.plane * sizeof(float), c->stream));
+  CU(cudaStreamSynchronize(c->stream));
   return RLTV_OK;
 }
 

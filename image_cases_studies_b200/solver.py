@@ -159,6 +159,15 @@ class Solver:
         nat.check(nat.lib.rltv_stage_gradk(self._ctx, nat.ptr(out)))
         return out
 
+    def stage_tv(self, order: int, norm: int, epsilon: float):
+        """TV norm map and divergence of the device-resident estimate (lib/deconvolution.pyx:137-239)."""
+        out = np.empty(self.u_shape, np.float32)
+        div = np.empty(self.u_shape, np.float32)
+        ms = C.c_float()
+        nat.check(nat.lib.rltv_stage_tv(self._ctx, int(order), int(norm), float(epsilon), nat.ptr(out), nat.ptr(div), C.byref(ms)))
+        self.last_tv_ms = float(ms.value)
+        return out, div
+
     def stage_whiteness(self, window) -> float:
         v = C.c_float()
         top, bottom, left, right = (int(x) for x in window)

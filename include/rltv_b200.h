@@ -154,6 +154,9 @@ int rltv_stage_residual(rltv_ctx* ctx, float* err_out /* packed HWC (M,N,3) */);
 int rltv_stage_adjoint(rltv_ctx* ctx, float* g_out /* packed HWC (M+MK-1, N+MK-1, 3) */);
 /* gk = valid-conv(rot180(u), err) (pyx:567-571) using the residual currently on device */
 int rltv_stage_gradk(rltv_ctx* ctx, float* gk_out /* packed (MK,MK,3) */);
+/* TV(u, out, M, N, epsilon, order, norm, div) (pyx:137-239) of the estimate on the device; order, norm in {1,2};
+ * out/div: packed HWC (M+MK-1, N+MK-1, 3), zero on the border ring; *ms = device time of the stencil kernel */
+int rltv_stage_tv(rltv_ctx* ctx, int32_t order, int32_t norm, float epsilon, float* out, float* div, float* ms);
 /* whiteness statistic of the residual window (pyx:627-638) */
 int rltv_stage_whiteness(rltv_ctx* ctx, int32_t top, int32_t bottom, int32_t left, int32_t right, float* M_r);
 

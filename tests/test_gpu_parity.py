@@ -196,3 +196,20 @@ def test_full_size_properties(dc):
     s.download(u2, p2)
     s.close()
     assert np.array_equal(u1, u2) and np.array_equal(p1, p2)
+
+
+@pytest.mark.parametrize("order,norm,eps", [(2, 1, 1e-2), (2, 2, 1e-2), (1, 1, 1e-6), (1, 2, 1e-6)])
+def test_tv_stencil_against_oracle(order, norm, eps):
+    """TV(u, out, ..., div) of lib/deconvolution.pyx:137-239 (the solver calls it with order 2, norm 1 and 2)."""
+    from image_cases_studies_b200.solver import Solver
+    from oracle import tv_oracle
+    rng = np.random.default_rng(order * 10 + norm)
+    M, N, K = 97, 203, 5
+    u = rng.random((M + K - 1, N + K - 1, 3), dtype=np.float32)
+    s = Solver(M, N, K)
+    s.upload(np.zeros((M, N, 3), np.float32), u, np.full((K, K, 3), 1 / 25, np.float32))
+    out, div = s.stage_tv(order, norm, eps)
+    s.close()
+    out_ref, div_ref = tv_oracle.tv(u, eps, order, norm)
+    assert rel_l2(out, out_ref) < 2e-6 and rel_l2(div, div_ref) < 2e-6
+    assert not out[0].any() and not out[:, 0].any() and not div[-1].any() and not div[:, -1].any()

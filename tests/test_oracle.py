@@ -84,3 +84,23 @@ def test_oracle_matches_live_reference(blind, K, shape):
     r = orc.richardson_lucy_MM(image, u0, psf0, *win, tau, *shape, 3, K, 3, 1e-3, 1e4, blind=blind)
     assert ref_loader.executed_iterations(log) == r.iterations == 3
     assert rel_l2(r.out, out) <= 2e-6 and psf_l1(r.psf, psf) <= 1e-5
+
+
+def test_tv_oracle_against_pure_loop_definition():
+    """oracle/tv_oracle.py against a literal per-pixel transcription of lib/deconvolution.pyx:159-172 (order 2, L1)."""
+    from oracle import tv_oracle
+    rng = np.random.default_rng(1)
+    u = rng.random((7, 9, 3))
+    out, div = tv_oracle.tv(u, 1e-2, 2, 1)
+    d = 2 ** 0.5
+    adjust = 4.0 * (1 + 1 / d)
+    for i in range(1, 6):
+        for j in range(1, 8):
+            for k in range(3):
+                udx = -2 * u[i, j, k] + u[i - 1, j, k] + u[i + 1, j, k]
+                udy = -2 * u[i, j, k] + u[i, j - 1, k] + u[i, j + 1, k]
+                udxdy = (-2 * u[i, j, k] + u[i - 1, j - 1, k] + u[i + 1, j + 1, k]) / d
+                udydx = (-2 * u[i, j, k] + u[i - 1, j + 1, k] + u[i + 1, j - 1, k]) / d
+                assert abs(div[i, j, k] - (-udx - udy - udxdy - udydx) / adjust) < 1e-14
+                assert abs(out[i, j, k] - (abs(udx) + abs(udy) + 1e-2 + abs(udxdy) + abs(udydx) + 1e-2) / adjust) < 1e-14
+    assert not out[0].any() and not div[:, -1].any()
