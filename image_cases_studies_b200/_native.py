@@ -67,6 +67,7 @@ SYMBOLS = [
     ("rltv_upload_band", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),
     ("rltv_download_rows", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     ("rltv_ipc_export", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("rltv_set_rank", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
     ("rltv_ipc_attach", C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32]),
     ("rltv_set_whiteness_owner", C.c_int, [C.c_void_p, C.c_int32]),
     ("rltv_enqueue_phase", C.c_int, [C.c_void_p, C.c_int32]),

@@ -32,7 +32,6 @@ using namespace rltv;
 namespace {
 
 thread_local std::string g_err;
-constexpr int NCH = 64;  // chunks of the cross-CTA PSF-gradient reduction
 
 int fail(int code, const std::string& msg) {
   g_err = msg;
@@ -72,14 +71,19 @@ struct rltv_ctx {
   int num_sms = 148;
   // TMA descriptors (rank-3 tensors x: Wu, y: rows, c: 3 over the planar arrays; boxes per kernel)
   CUtensorMap tm_u_conv{}, tm_err_conv{}, tm_img_epi{}, tm_u_epi{}, tm_ut_epi{}, tm_u_gk{}, tm_err_gk{};
-  double *gk_partial2 = nullptr, *gk_sum = nullptr;
-  // halo exchange
+  double* gk_sum = nullptr;
+  // row bands: halo exchange + all-gathers through peer memory (rltv_band.cuh)
   HaloSide side[2]{};           // 0: band above, 1: band below
-  void* peer_base[2] = {nullptr, nullptr};
-  unsigned* push_counter = nullptr;
-  int halo_seq = 0;             // pushes issued so far (identical on every band; never reset)
+  void* peer_base[MAXR] = {};
+  CommPeers peers{};            // peers.nranks == 1: whole frame or NCCL-baseline mode (no in-kernel exchange)
+  int rank = 0, world = 1;
+  bool fused_comm = false;      // true: in-kernel all-gathers over NVLink; false: host all-reduces (NCCL baseline)
+  unsigned* counters = nullptr; // [0] halo push, [1] adjoint, [2] gradk "last CTA" tickets
+  int halo_seq = 0;             // exchange numbers: identical on every band, never reset
+  int max_seq = 0, gk_seq = 0, stop_seq = 0;
   bool halo_pending = false;    // a push has been issued since the last wait
   bool white_owner = true;
+  int outer_since_begin = 0;
   // whiteness
   WhiteGeom wg{};
   double2 *Z = nullptr, *tw = nullptr;
@@ -201,12 +205,14 @@ int launch_conv_t(rltv_ctx* c, float lambd) {
   int grid = 2 * c->num_sms;
   if (grid > 3 * ntx * nty) grid = 3 * ntx * nty;
   ProfScope p(c, ADJ ? F_CONV_ADJ : F_CONV_FWD);
-  if (ADJ)
+  if (ADJ) {
+    if (c->peers.nranks > 1) c->max_seq += 1;
     k_conv<K, true><<<grid, C::THREADS, SMEM, c->stream>>>(c->tm_err_conv, c->tm_u_epi, c->tm_ut_epi, c->g, c->st, c->psf,
-                                                          lambd, c->gbuf, ntx, nty, y0, y1);
-  else
+                                                          lambd, c->gbuf, ntx, nty, y0, y1, c->peers, c->max_seq, c->counters + 1);
+  } else {
     k_conv<K, false><<<grid, C::THREADS, SMEM, c->stream>>>(c->tm_u_conv, c->tm_img_epi, c->tm_img_epi, c->g, c->st, c->psf,
-                                                           lambd, c->err, ntx, nty, y0, y1);
+                                                           lambd, c->err, ntx, nty, y0, y1, c->peers, 0, c->counters + 1);
+  }
   return RLTV_OK;
 }
 
@@ -215,18 +221,10 @@ int launch_gradk_t(rltv_ctx* c) {
   using C = GradkCfg<K>;
   CU(cudaFuncSetAttribute(k_gradk<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   const int ntx = (c->g.Wu + C::TW - 1) / C::TW, nty = (c->g.own1 - c->g.own0 + C::TH - 1) / C::TH;
-  {
-    ProfScope p(c, F_GRADK);
-    k_gradk<K><<<c->gk_nparts, C::THREADS, C::SMEM_BYTES, c->stream>>>(c->tm_u_gk, c->tm_err_gk, c->g, c->st, c->gk_partial, ntx, nty);
-  }
-  {
-    ProfScope p(c, F_GRADK);
-    k_gradk_reduce<NCH><<<dim3(NCH, 3), 256, 0, c->stream>>>(c->st, c->gk_partial, c->gk_nparts, K * K, c->gk_partial2);
-  }
-  {
-    ProfScope p(c, F_GRADK);
-    k_gradk_final<NCH><<<(3 * K * K + 255) / 256, 256, 0, c->stream>>>(c->st, c->gk_partial2, K * K, c->gk_sum);
-  }
+  if (c->peers.nranks > 1) c->gk_seq += 1;
+  ProfScope p(c, F_GRADK);
+  k_gradk<K><<<c->gk_nparts, C::THREADS, C::SMEM_BYTES, c->stream>>>(c->tm_u_gk, c->tm_err_gk, c->g, c->st, c->gk_partial, ntx, nty,
+                                                                     c->gk_sum, c->peers, c->gk_seq, c->counters + 2);
   return RLTV_OK;
 }
 
@@ -275,7 +273,8 @@ int launch_psf_update(rltv_ctx* c) {
   const int K = c->g.K;
   ProfScope p(c, F_PSF);
   k_psf_update<<<1, 256, 6 * K * K * sizeof(float), c->stream>>>(c->st, c->gk_sum, K, c->params.step_factor,
-                                                                c->params.correlation, c->psf, c->psf_caller);
+                                                                c->params.correlation, c->psf, c->psf_caller,
+                                                                c->peers.peer[c->rank], c->peers.nranks, c->gk_seq);
   return RLTV_OK;
 }
 
@@ -284,14 +283,14 @@ int launch_halo_push(rltv_ctx* c) {
   c->halo_seq += 1;
   c->halo_pending = true;
   ProfScope p(c, F_HALO);
-  k_halo_push<<<2 * c->num_sms, 256, 0, c->stream>>>(c->g, c->st, c->u, c->side[0], c->side[1], c->push_counter, c->halo_seq);
+  k_halo_push<<<2 * c->num_sms, 256, 0, c->stream>>>(c->g, c->st, c->u, c->side[0], c->side[1], c->counters + 0, c->halo_seq);
   return RLTV_OK;
 }
 
 int launch_halo_wait(rltv_ctx* c) {
   if (!c->halo_pending) return RLTV_OK;
   c->halo_pending = false;
-  const int* flags = reinterpret_cast<const int*>(reinterpret_cast<const char*>(c->u) + c->flag_offset);
+  const int* flags = reinterpret_cast<const Comm*>(reinterpret_cast<const char*>(c->u) + c->flag_offset)->halo_flag;
   ProfScope p(c, F_HALO);
   k_halo_wait<<<1, 32, 0, c->stream>>>(c->st, c->side[0].peer_u ? flags + 0 : nullptr,
                                        c->side[1].peer_u ? flags + 1 : nullptr, c->halo_seq);
@@ -406,7 +405,12 @@ int enqueue_phase(rltv_ctx* c, int phase) {
     case RLTV_PH_GRAD:
       if ((rc = launch_halo_wait(c)) != RLTV_OK) return rc;
       if ((rc = launch_conv_fwd(c)) != RLTV_OK) return rc;        // pyx:477-488
-      return launch_conv_adj(c, c->params.lambd);                 // pyx:490-491, :519, :524
+      if ((rc = launch_conv_adj(c, c->params.lambd)) != RLTV_OK) return rc;   // pyx:490-491, :519, :524
+      if (c->peers.nranks > 1) {
+        ProfScope p(c, F_HALO);
+        k_stepmax_gather<<<1, 32, 0, c->stream>>>(c->st, c->peers.peer[c->rank], c->peers.nranks, c->max_seq);
+      }
+      return RLTV_OK;
     case RLTV_PH_UPDATE:
       if ((rc = launch_update(c)) != RLTV_OK) return rc;          // pyx:527-531, :499-502, :552
       return launch_halo_push(c);
@@ -417,6 +421,19 @@ int enqueue_phase(rltv_ctx* c, int phase) {
     case RLTV_PH_PSF_STEP:
       return launch_psf_update(c);                                // pyx:574-589
     case RLTV_PH_OUTER_END:
+      c->outer_since_begin += 1;
+      if (c->peers.nranks > 1) {
+        c->stop_seq += 1;
+        if (!c->white_owner) {
+          ProfScope p(c, F_STATS);
+          k_stop_gather<<<1, 32, 0, c->stream>>>(c->st, c->peers.peer[c->rank], c->stop_seq);
+          return RLTV_OK;
+        }
+        if ((rc = launch_whiteness(c, 1)) != RLTV_OK) return rc;  // pyx:623-656
+        ProfScope p(c, F_STATS);
+        k_stop_publish<<<1, 32, 0, c->stream>>>(c->st, c->peers, c->stop_seq, c->outer_since_begin);
+        return RLTV_OK;
+      }
       return launch_whiteness(c, 1);                              // pyx:623-656
   }
   return fail(RLTV_ERR_ARG, "unknown phase");
@@ -521,7 +538,7 @@ int rltv_create_band(rltv_ctx** out, int32_t device, int32_t M, int32_t N, int32
   c->fwd1 = (b.row_hi == HuG) ? g.Hu : g.own1 + P;
   const size_t pb = 3 * g.plane * sizeof(float);
   c->flag_offset = (pb + 255) & ~size_t(255);
-  c->u_alloc_bytes = c->flag_offset + 256;
+  c->u_alloc_bytes = c->flag_offset + sizeof(Comm);
   if (cudaMalloc(&c->u, c->u_alloc_bytes) != cudaSuccess) { rltv_destroy(c); return fail(RLTV_ERR_ALLOC, "cudaMalloc of the estimate failed"); }
   CU(cudaMemsetAsync(c->u, 0, c->u_alloc_bytes, c->stream));
   float** planes[4] = {&c->ut, &c->gbuf, &c->img, &c->err};
@@ -536,8 +553,11 @@ int rltv_create_band(rltv_ctx** out, int32_t device, int32_t M, int32_t N, int32
   CU(cudaMalloc(&c->psf_hwc, kb));
   CU(cudaMalloc(&c->st, sizeof(State)));
   CU(cudaMemsetAsync(c->st, 0, sizeof(State), c->stream));
-  CU(cudaMalloc(&c->push_counter, sizeof(unsigned)));
-  CU(cudaMemsetAsync(c->push_counter, 0, sizeof(unsigned), c->stream));
+  CU(cudaMalloc(&c->counters, 4 * sizeof(unsigned)));
+  CU(cudaMemsetAsync(c->counters, 0, 4 * sizeof(unsigned), c->stream));
+  c->peers.nranks = 1;
+  c->peers.rank = 0;
+  c->peers.peer[0] = reinterpret_cast<Comm*>(reinterpret_cast<char*>(c->u) + c->flag_offset);
   CU(cudaMallocHost(&c->h_st, sizeof(State)));
   CU(cudaMallocHost(&c->h_poll, 4 * 2 * sizeof(int)));
   for (auto& e : c->poll_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -550,7 +570,6 @@ int rltv_create_band(rltv_ctx** out, int32_t device, int32_t M, int32_t N, int32
   }
   c->gk_nparts = c->num_sms;   // persistent k_gradk: one CTA per SM, one partial per CTA
   CU(cudaMalloc(&c->gk_partial, size_t(3) * c->gk_nparts * MK * MK * sizeof(float)));
-  CU(cudaMalloc(&c->gk_partial2, size_t(3) * NCH * MK * MK * sizeof(double)));
   CU(cudaMalloc(&c->gk_sum, size_t(3) * MK * MK * sizeof(double)));
   {
     int rc = make_maps(c);
@@ -573,9 +592,9 @@ int rltv_destroy(rltv_ctx* c) {
   float* f[] = {c->u, c->ut, c->gbuf, c->img, c->err, c->staging, c->psf, c->psf_caller, c->psf_hwc,
                 c->gk_partial, c->rowmin, c->rowmax, c->mr_out};
   for (auto p : f) cudaFree(p);
-  double* d[] = {c->gk_partial2, c->gk_sum, c->wa, c->wb, c->rowacc, c->rowsum};
+  double* d[] = {c->gk_sum, c->wa, c->wb, c->rowacc, c->rowsum};
   for (auto p : d) cudaFree(p);
-  cudaFree(c->Z); cudaFree(c->tw); cudaFree(c->st); cudaFree(c->push_counter);
+  cudaFree(c->Z); cudaFree(c->tw); cudaFree(c->st); cudaFree(c->counters);
   if (c->h_st) cudaFreeHost(c->h_st);
   if (c->h_poll) cudaFreeHost(c->h_poll);
   for (auto& e : c->poll_ev) if (e) cudaEventDestroy(e);
@@ -672,6 +691,7 @@ int rltv_begin(rltv_ctx* c, const rltv_params_t* p) {
   if (rc) return rc;
   CU(cudaMemsetAsync(c->st, 0, sizeof(State), c->stream));
   c->outer_enqueued = 0;
+  c->outer_since_begin = 0;
   c->launches = 0;
   for (int f = 0; f < F_COUNT; ++f) { c->prof_ms[f] = 0.f; c->prof_n[f] = 0; c->prof_used[f] = 0; }
   c->begun = true;
@@ -690,7 +710,7 @@ int rltv_enqueue_outer(rltv_ctx* c, int32_t n_outer) {
   int rc = check_ctx(c);
   if (rc) return rc;
   if (!c->begun) return fail(RLTV_ERR_STATE, "rltv_begin must precede rltv_enqueue_outer");
-  if (c->banded) return fail(RLTV_ERR_STATE, "row bands are stepped phase by phase (rltv_enqueue_phase)");
+  if (c->banded && !c->fused_comm) return fail(RLTV_ERR_STATE, "NCCL-baseline row bands are stepped phase by phase (rltv_enqueue_phase)");
   for (int i = 0; i < n_outer; ++i) {
     if ((rc = enqueue_outer(c)) != RLTV_OK) return rc;
     c->outer_enqueued++;
@@ -731,7 +751,7 @@ int rltv_finish(rltv_ctx* c, rltv_stats_t* stats) {
 }
 
 int rltv_solve(rltv_ctx* c, const rltv_params_t* p, rltv_stats_t* stats) {
-  if (c && c->banded) return fail(RLTV_ERR_STATE, "row bands are driven by the distributed host loop");
+  if (c && c->banded && !c->fused_comm) return fail(RLTV_ERR_STATE, "NCCL-baseline row bands are driven by the distributed host loop");
   int rc = rltv_begin(c, p);
   if (rc) return rc;
   // Host runs at most two outer iterations ahead of the device-side stop flag.
@@ -776,18 +796,42 @@ int rltv_ipc_export(rltv_ctx* c, void* handle64) {
   return RLTV_OK;
 }
 
-int rltv_ipc_attach(rltv_ctx* c, int32_t side, const void* handle64, int32_t peer_row_lo, int32_t peer_row_hi) {
+int rltv_set_rank(rltv_ctx* c, int32_t rank, int32_t world, int32_t fused) {
+  if (!c) return fail(RLTV_ERR_ARG, "null context");
+  if (world < 1 || world > MAXR || rank < 0 || rank >= world) return fail(RLTV_ERR_ARG, "bad rank/world (at most 8 bands)");
+  c->rank = rank;
+  c->world = world;
+  c->fused_comm = fused != 0;
+  Comm* mine = reinterpret_cast<Comm*>(reinterpret_cast<char*>(c->u) + c->flag_offset);
+  for (auto& p : c->peers.peer) p = nullptr;
+  c->peers.peer[c->fused_comm ? rank : 0] = mine;
+  c->peers.rank = c->fused_comm ? rank : 0;
+  c->peers.nranks = c->fused_comm ? world : 1;
+  if (!c->fused_comm) c->rank = 0;   // kernels index peers.peer[c->rank]; the NCCL baseline never exchanges in-kernel
+  return RLTV_OK;
+}
+
+int rltv_ipc_attach(rltv_ctx* c, int32_t peer_rank, const void* handle64, int32_t peer_row_lo, int32_t peer_row_hi) {
   int rc = check_ctx(c);
   if (rc) return rc;
-  if (side < 0 || side > 1 || !handle64) return fail(RLTV_ERR_ARG, "bad side/handle");
+  if (peer_rank < 0 || peer_rank >= MAXR || !handle64) return fail(RLTV_ERR_ARG, "bad peer rank/handle");
+  const int my_rank = c->fused_comm ? c->rank : c->peers.rank;
+  (void)my_rank;
   const int P2 = 2 * c->g.P;
   cudaIpcMemHandle_t h;
   std::memcpy(&h, handle64, 64);
   void* base = nullptr;
   CU(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
-  c->peer_base[side] = base;
+  c->peer_base[peer_rank] = base;
   const size_t peer_plane = size_t(peer_row_hi - peer_row_lo) * c->g.pitch;
   const size_t peer_flag_off = (3 * peer_plane * sizeof(float) + 255) & ~size_t(255);
+  Comm* pc = reinterpret_cast<Comm*>(reinterpret_cast<char*>(base) + peer_flag_off);
+  if (c->fused_comm) c->peers.peer[peer_rank] = pc;
+  // neighbours also exchange halos: the band above has row_hi inside my band, the band below has row_lo inside
+  int side = -1;
+  if (peer_row_hi > c->own_lo && peer_row_hi <= c->row_hi && peer_row_lo < c->row_lo) side = 0;   // band above
+  else if (peer_row_lo < c->own_hi && peer_row_lo >= c->row_lo && peer_row_hi > c->row_hi) side = 1;   // band below
+  if (side < 0) return RLTV_OK;
   HaloSide& s = c->side[side];
   s.peer_u = reinterpret_cast<float*>(base);
   s.peer_plane = peer_plane;
@@ -796,12 +840,12 @@ int rltv_ipc_attach(rltv_ctx* c, int32_t side, const void* handle64, int32_t pee
     // band above: its bottom halo = frame rows [own_lo, own_lo + 2P) = my first owned rows; I am ITS lower neighbour
     s.src_row = c->own_lo - c->row_lo;
     s.dst_row = c->own_lo - peer_row_lo;
-    s.peer_flag = reinterpret_cast<int*>(reinterpret_cast<char*>(base) + peer_flag_off) + 1;
+    s.peer_flag = &pc->halo_flag[1];
   } else {
     // band below: its top halo = frame rows [own_hi - 2P, own_hi) = my last owned rows; I am ITS upper neighbour
     s.src_row = c->own_hi - P2 - c->row_lo;
     s.dst_row = c->own_hi - P2 - peer_row_lo;
-    s.peer_flag = reinterpret_cast<int*>(reinterpret_cast<char*>(base) + peer_flag_off) + 0;
+    s.peer_flag = &pc->halo_flag[0];
   }
   if (s.src_row < c->g.own0 || s.src_row + s.nrows > c->g.own1 || s.dst_row < 0 || s.dst_row + s.nrows > peer_row_hi - peer_row_lo)
     return fail(RLTV_ERR_ARG, "halo rows do not fit: every band must own at least 2*(MK/2) rows");

@@ -1,6 +1,7 @@
 // Elementwise / reduction kernels of one inner step: the fused gradient-step + depth-of-field blend,
 // the PSF step + clip-and-normalise projection, and layout conversion at the host boundary.
 #pragma once
+#include "rltv_band.cuh"
 #include "rltv_common.cuh"
 
 namespace rltv {
@@ -55,8 +56,15 @@ k_update(Geom g, State* __restrict__ st, float* __restrict__ u, const float* __r
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_psf_update(State* __restrict__ st, const double* __restrict__ gk_sum, int K, float step, int correlation,
-             float* __restrict__ psf, float* __restrict__ psf_caller) {
+             float* __restrict__ psf, float* __restrict__ psf_caller, Comm* __restrict__ mine, int nranks, int seq) {
   if (st->stop) return;
+  const int par = seq & 1;
+  if (nranks > 1) {
+    // row bands: wait for every band's published PSF-gradient sums of this step (peer stores into `mine`)
+    if (threadIdx.x < nranks) spin_until(&mine->gk_flag[par][threadIdx.x], seq);
+    __syncthreads();
+    __threadfence_system();
+  }
   extern __shared__ float sm[];
   const int KK2 = K * K;
   float* gk = sm;              // [3][KK2]
@@ -70,7 +78,14 @@ k_psf_update(State* __restrict__ st, const double* __restrict__ gk_sum, int K, f
     const int c = i / KK2, q = i - c * KK2;
     const int qy = q / K, qx = q - qy * K;
     const int o = (K - 1 - qy) * K + (K - 1 - qx);
-    const float v = float(gk_sum[c * KK2 + o]);
+    double gsum;
+    if (nranks > 1) {
+      gsum = 0.0;                       // rank order: every band adds the same numbers in the same order
+      for (int r = 0; r < nranks; ++r) gsum += *reinterpret_cast<volatile double*>(&mine->gk_val[par][r][c * KK2 + o]);
+    } else {
+      gsum = gk_sum[c * KK2 + o];
+    }
+    const float v = float(gsum);
     gk[i] = v;
     const float p = psf[i];
     pk[i] = p;

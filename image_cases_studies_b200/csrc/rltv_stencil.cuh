@@ -15,6 +15,7 @@
 //   out[Y][X] = sum_{a,b} w[a][b] * in[Y-P+a][X-P+b]      (zero outside the plane)
 // with w = rot180(psf) for the forward blur (true convolution) and w = psf for the adjoint.
 #pragma once
+#include "rltv_band.cuh"
 #include "rltv_common.cuh"
 #include "rltv_tma.cuh"
 
@@ -140,7 +141,8 @@ template <int K, bool ADJ>
 __global__ void __launch_bounds__(ConvCfg<K>::THREADS, 2)
 k_conv(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_e0,
        const __grid_constant__ CUtensorMap tm_e1, Geom g, State* __restrict__ st, const float* __restrict__ psf,
-       float lambd, float* __restrict__ out, int ntx, int nty, int ybeg, int yend) {
+       float lambd, float* __restrict__ out, int ntx, int nty, int ybeg, int yend, CommPeers cp, int seq,
+       unsigned* __restrict__ done_counter) {
   using C = ConvCfg<K>;
   if (st->stop) return;
   extern __shared__ unsigned char smem_raw[];
@@ -273,6 +275,18 @@ k_conv(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtens
       }
     }
   }
+  if (ADJ && cp.nranks > 1) {
+    // row bands: the last CTA to finish publishes this band's step scalars to every band (peer stores)
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      if (atomicAdd(done_counter, 1u) == gridDim.x - 1) {
+        *done_counter = 0u;
+        __threadfence();
+        publish_step_max(st, cp, seq);
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -280,7 +294,7 @@ k_conv(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtens
 // Each lane owns a 4-pixel segment of the tile row, each warp a group of DYG displacement rows dy (and one
 // of RP row-parts of the tile).  The DYG*K accumulators per lane PERSIST across all the tiles a CTA walks for
 // one (channel, dy-chunk) work item and are reduced once (xor-butterfly over lanes, fixed-order sum over
-// row-parts); k_gradk_reduce / k_psf_update then sum the per-CTA partials in a fixed order: bit-reproducible.
+// row-parts); the last CTA to finish sums the per-CTA partials in CTA order (double): bit-reproducible.
 // ------------------------------------------------------------------------------------------------
 template <int K>
 struct GradkCfg {
@@ -358,7 +372,8 @@ struct GradkUnroll<K, N, N> {
 template <int K>
 __global__ void __launch_bounds__(GradkCfg<K>::THREADS, 1)
 k_gradk(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_e, Geom g,
-        const State* __restrict__ st, float* __restrict__ partial, int ntx, int nty) {
+        const State* __restrict__ st, float* __restrict__ partial, int ntx, int nty, double* __restrict__ gk_sum,
+        CommPeers cp, int seq, unsigned* __restrict__ done_counter) {
   using C = GradkCfg<K>;
   if (st->stop) return;
   extern __shared__ unsigned char smem_raw[];
@@ -457,33 +472,32 @@ k_gradk(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtens
       partial[(size_t(c) * gridDim.x + blockIdx.x) * K * K + r] = 0.f;
     }
   }
-}
-
-// Stage 1 of the cross-CTA reduction: partial2[c][chunk][o] = sum over the chunk's CTA partials (double).
-template <int NCH>
-__global__ void k_gradk_reduce(const State* __restrict__ st, const float* __restrict__ partial, int nparts, int KK2,
-                               double* __restrict__ partial2) {
-  if (st->stop) return;
-  const int c = blockIdx.y, chunk = blockIdx.x;
-  const int per = (nparts + NCH - 1) / NCH;
-  const int t0 = chunk * per, t1 = min(nparts, t0 + per);
-  for (int o = threadIdx.x; o < KK2; o += blockDim.x) {
-    double s = 0.0;
-    for (int t = t0; t < t1; ++t) s += double(partial[(size_t(c) * nparts + t) * KK2 + o]);
-    partial2[(size_t(c) * NCH + chunk) * KK2 + o] = s;
+  // The last CTA to finish sums the per-CTA partials in CTA order (double: deterministic whichever CTA is
+  // last) into gk_sum and, with row bands, publishes the band's sums to every band.
+  __threadfence();
+  __syncthreads();
+  __shared__ bool last;
+  if (tid == 0) last = (atomicAdd(done_counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  const int par = seq & 1;
+  for (int o = tid; o < 3 * K * K; o += C::THREADS) {
+    const int c = o / (K * K), r = o - c * K * K;
+    double sum = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b) sum += double(__ldcg(partial + (size_t(c) * gridDim.x + b) * K * K + r));
+    gk_sum[o] = sum;
+    if (cp.nranks > 1)
+      for (int rr = 0; rr < cp.nranks; ++rr) cp.peer[rr]->gk_val[par][cp.rank][o] = sum;
   }
-}
-
-// Stage 2: gk_sum[c][o] = sum over the NCH chunks, fixed order (double).  Row bands all-reduce this buffer.
-template <int NCH>
-__global__ void k_gradk_final(const State* __restrict__ st, const double* __restrict__ partial2, int KK2,
-                              double* __restrict__ gk_sum) {
-  if (st->stop) return;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 3 * KK2; i += gridDim.x * blockDim.x) {
-    const int c = i / KK2, o = i - c * KK2;
-    double s = 0.0;
-    for (int ch = 0; ch < NCH; ++ch) s += partial2[(size_t(c) * NCH + ch) * KK2 + o];
-    gk_sum[i] = s;
+  if (cp.nranks > 1) __threadfence_system();
+  __syncthreads();
+  if (tid == 0) {
+    *done_counter = 0u;
+    if (cp.nranks > 1) {
+      for (int rr = 0; rr < cp.nranks; ++rr) *reinterpret_cast<volatile int*>(&cp.peer[rr]->gk_flag[par][cp.rank]) = seq;
+      __threadfence_system();
+    }
   }
 }
 

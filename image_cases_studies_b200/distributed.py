@@ -4,16 +4,19 @@ One process per GPU (torchrun); every rank calls the same functions with the sam
 The padded estimate ``u`` is cut into contiguous row bands; each band also holds a halo of 2*(MK/2) rows of
 its neighbours.  Per inner step (lib/deconvolution.pyx:473-591):
 
-    GRAD      forward blur + adjoint on the band                       (CUDA kernels, csrc/)
-    all-reduce MAX of 6 int32      : max(u_c), max|G_c|   (pyx:524)    (NCCL through torch.distributed)
-    UPDATE    gradient step + blend, then the band PUSHES its edge rows into the neighbours' halos with peer
-              stores over NVLink (CUDA IPC mapping) and raises a step-numbered flag -- no NCCL, no host
-    PSF_GRAD  wait for the neighbours' flags, residual, PSF-gradient partial sums
-    all-reduce SUM of 3*MK*MK double : gradk  (pyx:571)                (NCCL)
-    PSF_STEP  identical tiny update on every rank (replicated PSF stays bit-identical)
+    GRAD      forward blur + adjoint on the band; the adjoint kernel's last CTA publishes the band's
+              max(u_c), max|G_c| (pyx:524) into every band's memory; a one-warp kernel gathers the max
+    UPDATE    gradient step + blend, then the band PUSHES its edge rows into the neighbours' halos
+    PSF_GRAD  wait for the neighbours' flags, residual, PSF-gradient partial sums; the last CTA publishes the
+              band's 3*MK*MK sums (pyx:571) to every band
+    PSF_STEP  waits for all bands' sums, adds them in rank order, identical tiny update on every rank
+              (the replicated PSF stays bit-identical without a broadcast)
 
-and once per outer iteration the band that holds the whiteness window evaluates the stop rule
-(pyx:623-654); an all-reduce MAX of one int32 spreads the stop flag.
+and once per outer iteration the band that holds the whiteness window evaluates the stop rule (pyx:623-654) and
+publishes the decision.  All of this is peer stores over NVLink into CUDA-IPC-mapped memory ordered by
+step-numbered flags (csrc/rltv_band.cuh): with ``comm="fused"`` (default) an outer iteration is a pure kernel
+sequence -- no NCCL, no host round trip.  ``comm="nccl"`` keeps the baseline in which the host all-reduces the
+three tiny buffers between phases through torch.distributed; it exists to measure what the fusion buys.
 """
 from __future__ import annotations
 
@@ -80,7 +83,7 @@ class _DevMem:
 class BandSolver:
     """One rank's band of a frame.  Needs an initialised torch.distributed NCCL process group."""
 
-    def __init__(self, M, N, MK, window, device=None, group=None):
+    def __init__(self, M, N, MK, window, device=None, group=None, comm="fused"):
         import torch
         import torch.distributed as dist
         self.torch, self.dist, self.group = torch, dist, group
@@ -95,16 +98,22 @@ class BandSolver:
         b = nat.Band(*self.band)
         nat.check(nat.lib.rltv_create_band(C.byref(self._ctx), self.device, self.M, self.N, self.MK, C.byref(b),
                                            C.c_void_p(self.tstream.cuda_stream)))
+        if comm not in ("fused", "nccl"):
+            raise ValueError("comm must be 'fused' or 'nccl'")
+        self.fused = comm == "fused"
         nat.check(nat.lib.rltv_set_whiteness_owner(self._ctx, int(self.rank == self.owner)))
-        # exchange CUDA IPC handles of the u allocations; map the neighbours' bands
+        nat.check(nat.lib.rltv_set_rank(self._ctx, self.rank, self.world, int(self.fused)))
+        # exchange CUDA IPC handles of the u allocations (they carry the halo flags and all-gather slots);
+        # fused: map every band, NCCL baseline: the two neighbours are enough
         h = (C.c_char * 64)()
         nat.check(nat.lib.rltv_ipc_export(self._ctx, h))
         handles = [None] * self.world
         dist.all_gather_object(handles, bytes(h.raw), group=group)
-        for side, peer in ((0, self.rank - 1), (1, self.rank + 1)):
-            if 0 <= peer < self.world:
-                hb = (C.c_char * 64).from_buffer_copy(handles[peer])
-                nat.check(nat.lib.rltv_ipc_attach(self._ctx, side, hb, self.bands[peer][0], self.bands[peer][1]))
+        for peer in range(self.world):
+            if peer == self.rank or (not self.fused and abs(peer - self.rank) != 1):
+                continue
+            hb = (C.c_char * 64).from_buffer_copy(handles[peer])
+            nat.check(nat.lib.rltv_ipc_attach(self._ctx, peer, hb, self.bands[peer][0], self.bands[peer][1]))
         dist.barrier(group=group)
         dev = f"cuda:{self.device}"
         def view(name, typestr, itemsize):
@@ -176,7 +185,14 @@ class BandSolver:
         nat.check(nat.lib.rltv_enqueue_phase(self._ctx, ph))
 
     def enqueue_outer(self, n: int = 1, first_it: int | None = None):
-        """Enqueue n outer iterations (phases + all-reduces) on this rank's stream; no host synchronisation."""
+        """Enqueue n outer iterations on this rank's stream; no host synchronisation."""
+        if self.fused:
+            with self.torch.cuda.stream(self.tstream):
+                for k in range(n):
+                    nat.check(nat.lib.rltv_enqueue_outer(self._ctx, 1))
+                    if first_it is not None:
+                        nat.check(nat.lib.rltv_poll_record(self._ctx, first_it + k))
+            return
         dist, group = self.dist, self.group
         MAX, SUM = dist.ReduceOp.MAX, dist.ReduceOp.SUM
         blind = bool(self.params.blind)
@@ -235,11 +251,11 @@ class BandSolver:
 
 
 def richardson_lucy_MM(image, u, psf, top, bottom, left, right, tau, M, N, C_, MK, iterations, step_factor, lambd,
-                       blind=True, correlation=False, group=None, **ignored):
+                       blind=True, correlation=False, group=None, comm="fused", **ignored):
     """SPMD drop-in: every rank of the process group calls this with the same arrays; on return every rank's ``u``
     and ``psf`` hold the full result, exactly as the single-GPU ``lib.deconvolution.richardson_lucy_MM`` leaves them."""
     M, N, MK = int(M), int(N), int(MK)
-    s = BandSolver(M, N, MK, (top, bottom, left, right), group=group)
+    s = BandSolver(M, N, MK, (top, bottom, left, right), group=group, comm=comm)
     try:
         s.upload(image, u, psf)
         params = Solver.make_params((top, bottom, left, right), tau, iterations, step_factor, lambd, blind, correlation)

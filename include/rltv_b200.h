@@ -129,10 +129,14 @@ int rltv_upload_band(rltv_ctx* ctx, const float* image_rows, size_t image_row_st
 /* copies u rows [row0, row0+nrows) (frame coordinates, must be held by this band) to the host */
 int rltv_download_rows(rltv_ctx* ctx, float* u_rows, size_t u_row_stride_bytes, int32_t row0, int32_t nrows,
                        float* psf_caller, float* psf_refined);
-/* CUDA IPC: `handle` is a 64-byte cudaIpcMemHandle_t of this band's u allocation (which also carries the
- * halo flags).  side 0 = the band above (previous rank), 1 = the band below. */
+/* rank / world of this band; fused != 0: step scalars, PSF-gradient sums and the stop flag are exchanged by the
+ * kernels themselves through peer memory (no NCCL, rltv_enqueue_outer / rltv_solve work on the band);
+ * fused == 0: the host all-reduces rltv_device_ptr buffers between phases (NCCL baseline).  Call before attach. */
+int rltv_set_rank(rltv_ctx* ctx, int32_t rank, int32_t world, int32_t fused);
+/* CUDA IPC: `handle` is a 64-byte cudaIpcMemHandle_t of a band's u allocation (which also carries its halo flags
+ * and all-gather slots).  Attach every other band (fused) or at least the two neighbours (NCCL baseline). */
 int rltv_ipc_export(rltv_ctx* ctx, void* handle64);
-int rltv_ipc_attach(rltv_ctx* ctx, int32_t side, const void* handle64, int32_t peer_row_lo, int32_t peer_row_hi);
+int rltv_ipc_attach(rltv_ctx* ctx, int32_t peer_rank, const void* handle64, int32_t peer_row_lo, int32_t peer_row_hi);
 /* exactly one band evaluates the whiteness statistic / stop rule (the one holding the window rows) */
 int rltv_set_whiteness_owner(rltv_ctx* ctx, int32_t owner);
 /* one outer iteration = BEGIN, 5 x (GRAD, [all-reduce MAX step_max], UPDATE, blind: PSF_GRAD,

@@ -25,12 +25,13 @@ def main():
     report = {}
     cases = [("c2_blind_2mp_k9", 0.35, 4, False), ("c1_nonblind_512_g5", 1.0, 3, False),
              ("c3_blind_24mp_k15", 0.12, 2, True)]
+    comm = os.environ.get("RLTV_COMM", "fused")
     for name, scale, iters, corr in cases:
         c = synthetic.make_case(name, seed=11, scale=scale, iterations=iters)
         M, N = c.shape
         u_d, psf_d = c.u0.copy(), c.psf0.copy()
         out_d = distributed.richardson_lucy_MM(c.image, u_d, psf_d, *c.window, c.tau, M, N, 3, c.MK, c.iterations,
-                                               c.step_factor, c.lambd, blind=c.blind, correlation=corr)
+                                               c.step_factor, c.lambd, blind=c.blind, correlation=corr, comm=comm)
         st_d = distributed.richardson_lucy_MM.last_stats
         ok = True
         if rank == 0:
@@ -46,7 +47,7 @@ def main():
             # identical algorithm, different summation order of the PSF gradient only
             ok = (r["rel_u"] <= 1e-6 and r["psf"] <= 1e-6 and r["its"][0] == r["its"][1] and r["mr"] <= 1e-5
                   and r["moved"] > 1e-7)
-            print(name, M, N, c.MK, r, "OK" if ok else "FAIL", flush=True)
+            print(comm, name, M, N, c.MK, r, "OK" if ok else "FAIL", flush=True)
         flag = torch.tensor([0 if ok else 1], device=f"cuda:{local}")
         dist.all_reduce(flag)
         # every rank must hold the same full result
