@@ -202,7 +202,7 @@ int launch_conv_t(rltv_ctx* c, float lambd) {
   CU(cudaFuncSetAttribute(k_conv<K, ADJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
   const int y0 = ADJ ? c->g.own0 : c->fwd0, y1 = ADJ ? c->g.own1 : c->fwd1;
   const int ntx = (c->g.pitch + C::TW - 1) / C::TW, nty = (y1 - y0 + C::TH - 1) / C::TH;
-  int grid = 2 * c->num_sms;
+  int grid = C::CTAS_PER_SM * c->num_sms;
   if (grid > 3 * ntx * nty) grid = 3 * ntx * nty;
   ProfScope p(c, ADJ ? F_CONV_ADJ : F_CONV_FWD);
   if (ADJ) {

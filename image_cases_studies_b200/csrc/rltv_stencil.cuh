@@ -30,10 +30,13 @@ template <int K>
 struct ConvCfg {
   static constexpr int X = 4;                       // outputs per thread along x (one float4)
   static constexpr int R = (K <= 17) ? 4 : 2;       // output rows per thread == depth of the rolling window
-  static constexpr int WARPS = 8;
+  // 4 warps x 4 rows: 128x16-output tiles, 4 CTAs per SM.  Small tiles keep the static schedule balanced when a
+  // row band is only ~500 rows tall (8 GPUs), and four independent load/compute pipelines per SM overlap better.
+  static constexpr int WARPS = (K <= 17) ? 4 : 8;
+  static constexpr int CTAS_PER_SM = (K <= 17) ? 4 : 2;
   static constexpr int THREADS = 32 * WARPS;
   static constexpr int TW = 32 * X;                 // 128 output columns per tile
-  static constexpr int TH = WARPS * R;              // 32 (or 16) output rows per tile
+  static constexpr int TH = WARPS * R;              // 16 output rows per tile
   static constexpr int P = K / 2;
   // The TMA unit requires the box start to be 16-byte aligned along x (measured: tools/tma_test.cu), so the
   // tile starts P4 = roundup(P, 4) columns left of the outputs and every window index is shifted by DELTA.
@@ -138,7 +141,7 @@ __device__ __forceinline__ void stencil_core(const float* __restrict__ tile, con
 // Tiles are numbered x-fastest inside a channel; CTA b processes tiles b, b+grid, b+2*grid, ...
 // ------------------------------------------------------------------------------------------------
 template <int K, bool ADJ>
-__global__ void __launch_bounds__(ConvCfg<K>::THREADS, 2)
+__global__ void __launch_bounds__(ConvCfg<K>::THREADS, ConvCfg<K>::CTAS_PER_SM)
 k_conv(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_e0,
        const __grid_constant__ CUtensorMap tm_e1, Geom g, State* __restrict__ st, const float* __restrict__ psf,
        float lambd, float* __restrict__ out, int ntx, int nty, int ybeg, int yend, CommPeers cp, int seq,
@@ -484,8 +487,19 @@ k_gradk(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtens
   const int par = seq & 1;
   for (int o = tid; o < 3 * K * K; o += C::THREADS) {
     const int c = o / (K * K), r = o - c * K * K;
-    double sum = 0.0;
-    for (unsigned b = 0; b < gridDim.x; ++b) sum += double(__ldcg(partial + (size_t(c) * gridDim.x + b) * K * K + r));
+    // 8 independent accumulators (CTA b goes to accumulator b % 8): 8+ loads in flight per thread, fixed tree
+    double a8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const float* src = partial + size_t(c) * gridDim.x * K * K + r;
+    unsigned b = 0;
+    for (; b + 8 <= gridDim.x; b += 8) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = __ldcg(src + size_t(b + j) * K * K);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a8[j] += double(v[j]);
+    }
+    for (; b < gridDim.x; ++b) a8[b & 7] += double(__ldcg(src + size_t(b) * K * K));
+    const double sum = ((a8[0] + a8[1]) + (a8[2] + a8[3])) + ((a8[4] + a8[5]) + (a8[6] + a8[7]));
     gk_sum[o] = sum;
     if (cp.nranks > 1)
       for (int rr = 0; rr < cp.nranks; ++rr) cp.peer[rr]->gk_val[par][cp.rank][o] = sum;

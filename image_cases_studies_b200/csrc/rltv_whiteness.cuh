@@ -185,13 +185,16 @@ __global__ void k_white_rows_inv(const State* __restrict__ st, WhiteGeom wg, con
 __global__ void k_outer_finalize(State* __restrict__ st, WhiteGeom wg, const double* __restrict__ rowacc,
                                  int blind, float tau, int advance, int owner, float* __restrict__ out) {
   if (st->stop) return;
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (blockIdx.x != 0) return;
   if (!owner) {
-    if (advance) st->it = st->it + 1;
+    if (advance && threadIdx.x == 0) st->it = st->it + 1;
     return;
   }
+  // one warp: lane-strided partial sums, fixed butterfly (deterministic)
   double t = 0.0;
-  for (int i = 0; i < 3 * wg.h; ++i) t += rowacc[i];
+  for (int i = threadIdx.x; i < 3 * wg.h; i += 32) t += rowacc[i];
+  t = warp_sum(t);
+  if (threadIdx.x != 0) return;
   const float M_r = float(t / (3.0 * double(wg.h) * double(wg.w)));   // np.mean(test), pyx:638
   if (out) *out = M_r;
   if (!advance) return;
