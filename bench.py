@@ -225,6 +225,9 @@ def main():
         solver.upload(case.image, case.u0, case.psf0)
 
     # ---- device-resident steps (value) -------------------------------------------------------------
+    # The blind stop rule fires after 3 outer iterations on some synthetic inputs (it is data dependent); the
+    # timed steady-state steps keep evaluating it but do not act on it.  The e2e call below obeys it.
+    solver.ignore_stop(True)
     with torch.cuda.stream(stream):
         solver.begin(params)
         with ClockSampler(dev) as clocks:          # sampled under the same load: warm-up, timed steps, untimed tail
@@ -344,7 +347,8 @@ def main():
                             f"one frame in {world} row bands, one per GPU: halo rows by NVLink peer stores, NCCL all-reduce of "
                             "6 step scalars + 3*MK^2 PSF-gradient sums per inner step (baseline)"),
                            "l2": "working set (5 planar frame copies, 1.4 GB) far exceeds the 126 MB L2; no flush needed",
-                           "all_steps_live": valid_steps},
+                           "all_steps_live": valid_steps,
+                           "stop_rule": "evaluated every step, not acted upon in the timed region (obeyed in e2e)"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_timed,
                 "clocks": clocks.summary()}
         print(json.dumps(line))

@@ -61,6 +61,7 @@ SYMBOLS = [
     ("rltv_enqueue_outer", C.c_int, [C.c_void_p, C.c_int32]),
     ("rltv_finish", C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     ("rltv_stream", C.c_void_p, [C.c_void_p]),
+    ("rltv_set_ignore_stop", C.c_int, [C.c_void_p, C.c_int32]),
     ("rltv_profile_enable", C.c_int, [C.c_void_p, C.c_int32]),
     ("rltv_profile_get", C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     ("rltv_create_band", C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(Band), C.c_void_p]),

@@ -83,6 +83,7 @@ struct rltv_ctx {
   int max_seq = 0, gk_seq = 0, stop_seq = 0;
   bool halo_pending = false;    // a push has been issued since the last wait
   bool white_owner = true;
+  bool ignore_stop = false;     // benchmark stepping only: evaluate the stop rule, do not act on it
   int outer_since_begin = 0;
   // whiteness
   WhiteGeom wg{};
@@ -429,12 +430,12 @@ int enqueue_phase(rltv_ctx* c, int phase) {
           k_stop_gather<<<1, 32, 0, c->stream>>>(c->st, c->peers.peer[c->rank], c->stop_seq);
           return RLTV_OK;
         }
-        if ((rc = launch_whiteness(c, 1)) != RLTV_OK) return rc;  // pyx:623-656
+        if ((rc = launch_whiteness(c, c->ignore_stop ? 2 : 1)) != RLTV_OK) return rc;  // pyx:623-656
         ProfScope p(c, F_STATS);
         k_stop_publish<<<1, 32, 0, c->stream>>>(c->st, c->peers, c->stop_seq, c->outer_since_begin);
         return RLTV_OK;
       }
-      return launch_whiteness(c, 1);                              // pyx:623-656
+      return launch_whiteness(c, c->ignore_stop ? 2 : 1);                              // pyx:623-656
   }
   return fail(RLTV_ERR_ARG, "unknown phase");
 }
@@ -849,6 +850,12 @@ int rltv_ipc_attach(rltv_ctx* c, int32_t peer_rank, const void* handle64, int32_
   }
   if (s.src_row < c->g.own0 || s.src_row + s.nrows > c->g.own1 || s.dst_row < 0 || s.dst_row + s.nrows > peer_row_hi - peer_row_lo)
     return fail(RLTV_ERR_ARG, "halo rows do not fit: every band must own at least 2*(MK/2) rows");
+  return RLTV_OK;
+}
+
+int rltv_set_ignore_stop(rltv_ctx* c, int32_t on) {
+  if (!c) return fail(RLTV_ERR_ARG, "null context");
+  c->ignore_stop = on != 0;
   return RLTV_OK;
 }
 

@@ -205,10 +205,12 @@ __global__ void k_outer_finalize(State* __restrict__ st, WhiteGeom wg, const dou
   st->n_hist = min(it + 1, 4096);
   if (it > 1) {                                                        // pyx:643
     const float prev = st->M_r_prev;
+    // advance == 2: benchmark stepping -- the rule is evaluated but not acted upon, so that steady-state steps can
+    // be timed on inputs whose rule would fire early (never used by the drop-in entry points)
     if (blind) {
-      if (M_r > prev) st->stop = 1;                                    // pyx:646-647
+      if (M_r > prev && advance == 1) st->stop = 1;                    // pyx:646-647
     } else {
-      if ((M_r - prev) / (M_r + prev) > tau) st->stop = 1;             // pyx:652-653
+      if ((M_r - prev) / (M_r + prev) > tau && advance == 1) st->stop = 1;   // pyx:652-653
     }
   }
   st->it = it + 1;                                                     // pyx:656

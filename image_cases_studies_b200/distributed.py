@@ -238,6 +238,9 @@ class BandSolver:
             self.enqueue_outer(1, first_it=it)
         return self.finish()
 
+    def ignore_stop(self, on=True):
+        nat.check(nat.lib.rltv_set_ignore_stop(self._ctx, int(on)))
+
     def profile_enable(self, on=True):
         nat.check(nat.lib.rltv_profile_enable(self._ctx, int(on)))
 

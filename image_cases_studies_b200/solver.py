@@ -132,6 +132,10 @@ class Solver:
     def stream(self) -> int:
         return int(nat.lib.rltv_stream(self._ctx) or 0)
 
+    def ignore_stop(self, on: bool = True):
+        """Benchmark stepping: evaluate the stop rule but keep iterating (see include/rltv_b200.h)."""
+        nat.check(nat.lib.rltv_set_ignore_stop(self._ctx, int(on)))
+
     def profile_enable(self, on: bool = True):
         nat.check(nat.lib.rltv_profile_enable(self._ctx, int(on)))
 

@@ -107,6 +107,9 @@ int rltv_finish(rltv_ctx* ctx, rltv_stats_t* stats);
 void* rltv_stream(rltv_ctx* ctx);
 /* Time (ms, CUDA events on the context's stream) and launch count of each kernel family since the last
  * rltv_begin, for bench.py's roofline.  names: "conv_fwd","conv_adj","update","gradk","psf","stats","copy". */
+/* Benchmark stepping only: the stop rule (pyx:643-654) is still evaluated every outer iteration but not acted
+ * upon, so that steady-state iterations can be timed on inputs whose rule fires after 3 iterations. */
+int rltv_set_ignore_stop(rltv_ctx* ctx, int32_t on);
 int rltv_profile_enable(rltv_ctx* ctx, int32_t on);
 int rltv_profile_get(rltv_ctx* ctx, const char* family, float* total_ms, int32_t* launches);
 
