@@ -213,3 +213,22 @@ def test_tv_stencil_against_oracle(order, norm, eps):
     out_ref, div_ref = tv_oracle.tv(u, eps, order, norm)
     assert rel_l2(out, out_ref) < 2e-6 and rel_l2(div, div_ref) < 2e-6
     assert not out[0].any() and not out[:, 0].any() and not div[-1].any() and not div[:, -1].any()
+
+
+def test_pyramid_driver_on_gpu_matches_oracle_driven_flow(tmp_path):
+    """deblur_module (deconvolve.py:65-368) end to end: the same driver run with the B200 solver and with the oracle."""
+    from image_cases_studies_b200 import deconvolve as drv
+    from image_cases_studies_b200.lib import utils
+    from oracle import rl_mm_oracle as orc
+    from test_driver import OracleSolver
+    rng = np.random.default_rng(8)
+    sharp = rng.random((90, 110, 3)) * 200 + 20
+    k = utils.gaussian_kernel(5, 1.2)
+    blurred = np.stack([orc.conv2(np.pad(sharp[..., c], 2, mode="edge"), k, "valid") for c in range(3)], axis=2)
+    kw = dict(mask=[45, 55], mask_size=41, iterations=3, display=False, save=False)
+    out_gpu = drv.deblur_module(blurred, "g", str(tmp_path), 5, **kw)
+    psf_gpu = drv.deblur_module.last_psf.copy()
+    out_ref = drv.deblur_module(blurred, "r", str(tmp_path), 5, solver=OracleSolver, **kw)
+    psf_ref = drv.deblur_module.last_psf.copy()
+    assert rel_l2(out_gpu, out_ref) <= TOL_IMAGE_REL_L2
+    assert psf_l1(psf_gpu, psf_ref) <= TOL_PSF_L1
