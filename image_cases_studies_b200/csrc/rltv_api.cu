@@ -377,16 +377,14 @@ int launch_whiteness(rltv_ctx* c, int advance) {
   const int fft_threads = L / 2 < 32 ? 32 : L / 2;
   const size_t fft_smem = size_t(L) * sizeof(double2);
   CU(cudaFuncSetAttribute(k_white_rows_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * 16));
-  CU(cudaFuncSetAttribute(k_white_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * 16));
+  CU(cudaFuncSetAttribute(k_white_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * 16 + 1024 * 16));
   CU(cudaFuncSetAttribute(k_white_rows_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * 16));
   { ProfScope p(c, F_STATS);
-    k_win_rows<<<dim3(wg.h, 3), 128, 0, c->stream>>>(c->g, c->st, c->err, wg, c->rowsum, c->rowmin, c->rowmax); }
-  { ProfScope p(c, F_STATS);
-    k_win_final<<<1, 256, 0, c->stream>>>(c->st, wg, c->rowsum, c->rowmin, c->rowmax); }
+    k_win_rows<<<dim3(wg.h, 3), 128, 0, c->stream>>>(c->g, c->st, c->err, wg, c->rowsum, c->rowmin, c->rowmax, c->counters + 3); }
   { ProfScope p(c, F_STATS);
     k_white_rows_fwd<<<dim3(wg.h, 3), fft_threads, fft_smem, c->stream>>>(c->g, c->st, c->err, wg, c->tw, c->Z); }
   { ProfScope p(c, F_STATS);
-    k_white_cols<<<dim3(L, 3), fft_threads, fft_smem, c->stream>>>(c->st, wg, c->tw, c->Z); }
+    k_white_cols<<<dim3(L / 2 + 1, 3), fft_threads, fft_smem + size_t(L / 2) * sizeof(double2), c->stream>>>(c->st, wg, c->tw, c->Z); }
   { ProfScope p(c, F_STATS);
     k_white_rows_inv<<<dim3(wg.h, 3), fft_threads, fft_smem, c->stream>>>(c->st, wg, c->tw, c->Z, c->wa, c->wb, c->rowacc); }
   { ProfScope p(c, F_STATS);

@@ -21,9 +21,11 @@ struct WhiteGeom {
 };
 
 // S1a: per (window row, channel) partial sum / min / max of the residual window. block = 128 threads.
+// The last block to finish reduces the per-row partials in row order (deterministic) into the State.
 __global__ void __launch_bounds__(128)
-k_win_rows(Geom g, const State* __restrict__ st, const float* __restrict__ err, WhiteGeom wg,
-           double* __restrict__ rowsum, float* __restrict__ rowmin, float* __restrict__ rowmax) {
+k_win_rows(Geom g, State* __restrict__ st, const float* __restrict__ err, WhiteGeom wg,
+           double* __restrict__ rowsum, float* __restrict__ rowmin, float* __restrict__ rowmax,
+           unsigned* __restrict__ done_counter) {
   if (st->stop) return;
   const int y = blockIdx.x, c = blockIdx.y;
   const float* row = err + size_t(c) * g.plane + size_t(wg.top + g.P - g.row0 + y) * g.pitch + (wg.left + g.P);
@@ -39,33 +41,31 @@ k_win_rows(Geom g, const State* __restrict__ st, const float* __restrict__ err, 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (lane == 0) { ss[warp] = s; smn[warp] = mn; smx[warp] = mx; }
   __syncthreads();
+  __shared__ bool last;
   if (threadIdx.x == 0) {
     rowsum[c * wg.h + y] = (ss[0] + ss[1]) + (ss[2] + ss[3]);
     rowmin[c * wg.h + y] = fminf(fminf(smn[0], smn[1]), fminf(smn[2], smn[3]));
     rowmax[c * wg.h + y] = fmaxf(fmaxf(smx[0], smx[1]), fmaxf(smx[2], smx[3]));
+    __threadfence();
+    last = (atomicAdd(done_counter, 1u) == gridDim.x * gridDim.y - 1);
   }
-}
-
-// S1b: one block: window mean and 1/max|E - mean| into the state.
-__global__ void __launch_bounds__(256)
-k_win_final(State* __restrict__ st, WhiteGeom wg, const double* __restrict__ rowsum,
-            const float* __restrict__ rowmin, const float* __restrict__ rowmax) {
-  if (st->stop) return;
-  __shared__ double ss[8];
-  __shared__ float smn[8], smx[8];
-  double s = 0.0;
-  float mn = INFINITY, mx = -INFINITY;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  double s2 = 0.0;
+  float mn2 = INFINITY, mx2 = -INFINITY;
   for (int i = threadIdx.x; i < 3 * wg.h; i += blockDim.x) {
-    s += rowsum[i]; mn = fminf(mn, rowmin[i]); mx = fmaxf(mx, rowmax[i]);
+    s2 += __ldcg(rowsum + i); mn2 = fminf(mn2, __ldcg(rowmin + i)); mx2 = fmaxf(mx2, __ldcg(rowmax + i));
   }
-  s = warp_sum(s); mn = warp_min(mn); mx = warp_max(mx);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) { ss[warp] = s; smn[warp] = mn; smx[warp] = mx; }
+  s2 = warp_sum(s2); mn2 = warp_min(mn2); mx2 = warp_max(mx2);
+  __syncthreads();
+  if (lane == 0) { ss[warp] = s2; smn[warp] = mn2; smx[warp] = mx2; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    double t = 0.0; float a = INFINITY, b = -INFINITY;
-    for (int i = 0; i < 8; ++i) { t += ss[i]; a = fminf(a, smn[i]); b = fmaxf(b, smx[i]); }
-    st->win_sum = t; st->win_min = a; st->win_max = b;
+    st->win_sum = (ss[0] + ss[1]) + (ss[2] + ss[3]);
+    st->win_min = fminf(fminf(smn[0], smn[1]), fminf(smn[2], smn[3]));
+    st->win_max = fmaxf(fmaxf(smx[0], smx[1]), fmaxf(smx[2], smx[3]));
+    *done_counter = 0u;
   }
 }
 
@@ -74,8 +74,8 @@ __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
 }
 
 // In-place radix-2 DIT FFT of s[0..L) (already in bit-reversed order), L/2 threads cooperate.
-// tw[k] = exp(-2 pi i k / L); inverse uses the conjugate.  Unnormalised.
-__device__ __forceinline__ void fft_smem(double2* s, const double2* __restrict__ tw, int L, int log2L, bool inverse) {
+// tw[k] = exp(-2 pi i k / L) (global or shared memory); inverse uses the conjugate.  Unnormalised.
+__device__ __forceinline__ void fft_smem(double2* s, const double2* tw, int L, int log2L, bool inverse) {
   const int j = threadIdx.x;
   for (int stage = 1; stage <= log2L; ++stage) {
     const int half = 1 << (stage - 1);
@@ -114,11 +114,15 @@ __global__ void k_white_rows_fwd(Geom g, const State* __restrict__ st, const flo
 }
 
 // S4: block (kx, c): column forward FFT (rows >= h are zero), |.|^2, inverse FFT; result back into Z.
-__global__ void k_white_cols(const State* __restrict__ st, WhiteGeom wg, const double2* __restrict__ tw,
+// Only kx in [0, L/2] is launched: the window is real, so its power spectrum P is real with P[ky][L-kx] =
+// P[L-ky][kx], and the column-inverse transform obeys Z'[dy][L-kx] = conj(Z'[dy][kx]); k_white_rows_inv mirrors.
+__global__ void k_white_cols(const State* __restrict__ st, WhiteGeom wg, const double2* __restrict__ tw_g,
                              double2* __restrict__ Z) {
   if (st->stop) return;
   extern __shared__ double2 sd[];
   const int kx = blockIdx.x, c = blockIdx.y, L = wg.L;
+  double2* tw = sd + L;                                     // twiddles once per block in shared memory
+  for (int i = threadIdx.x; i < L / 2; i += blockDim.x) tw[i] = tw_g[i];
   double2* col = Z + size_t(c) * L * L + kx;
   for (int i = threadIdx.x; i < L; i += blockDim.x) {
     const int r = __brev(unsigned(i)) >> (32 - wg.log2L);
@@ -156,7 +160,16 @@ __global__ void k_white_rows_inv(const State* __restrict__ st, WhiteGeom wg, con
   int dy = (wg.h - 1) - (n + (wg.h - 1) / 2);
   if (dy < 0) dy += L;
   const double2* in = Z + (size_t(c) * L + dy) * L;
-  for (int i = threadIdx.x; i < L; i += blockDim.x) sd[__brev(unsigned(i)) >> (32 - wg.log2L)] = in[i];
+  for (int i = threadIdx.x; i < L; i += blockDim.x) {
+    double2 v;
+    if (i <= L / 2) {
+      v = in[i];
+    } else {                                                // columns kx > L/2 were not computed: conjugate mirror
+      v = in[L - i];
+      v.y = -v.y;
+    }
+    sd[__brev(unsigned(i)) >> (32 - wg.log2L)] = v;
+  }
   __syncthreads();
   fft_smem(sd, tw, L, wg.log2L, true);
   const double inv = 1.0 / (double(L) * double(L));
