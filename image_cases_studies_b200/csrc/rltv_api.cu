@@ -15,6 +15,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -23,7 +24,9 @@
 #include "rltv_band.cuh"
 #include "rltv_common.cuh"
 #include "rltv_elementwise.cuh"
+#include "rltv_fft.cuh"
 #include "rltv_stencil.cuh"
+#include "rltv_stencil_fft.cuh"
 #include "rltv_tv.cuh"
 #include "rltv_whiteness.cuh"
 
@@ -71,6 +74,10 @@ struct rltv_ctx {
   int num_sms = 148;
   // TMA descriptors (rank-3 tensors x: Wu, y: rows, c: 3 over the planar arrays; boxes per kernel)
   CUtensorMap tm_u_conv{}, tm_err_conv{}, tm_img_epi{}, tm_u_epi{}, tm_ut_epi{}, tm_u_gk{}, tm_err_gk{};
+  // row-FFT hybrid stencils (K <= 17): boxes 128 x (64+K-1) for the input, 112 x 64 for the epilogue operands
+  CUtensorMap tm_u_fft{}, tm_err_fft{}, tm_img_fepi{}, tm_u_fepi{}, tm_ut_fepi{};
+  float2* wspec = nullptr;      // tap spectra [2][3][K][128]
+  bool use_fft = false;
   double* gk_sum = nullptr;
   // row bands: halo exchange + all-gathers through peer memory (rltv_band.cuh)
   HaloSide side[2]{};           // 0: band above, 1: band below
@@ -192,12 +199,53 @@ int make_maps_t(rltv_ctx* c) {
   if ((rc = make_tmap(&c->tm_u_gk, c->u, g, g.Hu, G::SP, G::SROWS))) return rc;
   // residual as seen by the PSF gradient: OWNED rows only (halo rows read as zero)
   if ((rc = make_tmap(&c->tm_err_gk, c->err + size_t(g.own0) * g.pitch, g, g.own1 - g.own0, G::TW, G::TH))) return rc;
+  if constexpr (K >= 9 && K <= 17) {
+    using F = FftCfg<K>;
+    if ((rc = make_tmap(&c->tm_u_fft, c->u, g, g.Hu, FFT_N, F::IN_ROWS))) return rc;
+    if ((rc = make_tmap(&c->tm_err_fft, c->err, g, g.Hu, FFT_N, F::IN_ROWS))) return rc;
+    if ((rc = make_tmap(&c->tm_img_fepi, c->img, g, g.Hu, F::TWO, F::TROWS))) return rc;
+    if ((rc = make_tmap(&c->tm_u_fepi, c->u, g, g.Hu, F::TWO, F::TROWS))) return rc;
+    if ((rc = make_tmap(&c->tm_ut_fepi, c->ut, g, g.Hu, F::TWO, F::TROWS))) return rc;
+  }
+  return RLTV_OK;
+}
+
+template <int K, bool ADJ>
+int launch_conv_fft_t(rltv_ctx* c, float lambd) {
+  if constexpr (K >= 9 && K <= 17) {
+    using C = FftCfg<K>;
+    constexpr int SMEM = C::smem_bytes(ADJ);
+    CU(cudaFuncSetAttribute(k_conv_fft<K, ADJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    const int y0 = ADJ ? c->g.own0 : c->fwd0, y1 = ADJ ? c->g.own1 : c->fwd1;
+    const int ntx = (c->g.Wu + C::TWO - 1) / C::TWO, nty = (y1 - y0 + C::TROWS - 1) / C::TROWS;
+    int grid = c->num_sms;
+    if (grid > 3 * ntx * nty) grid = 3 * ntx * nty;
+    ProfScope p(c, ADJ ? F_CONV_ADJ : F_CONV_FWD);
+    if (ADJ) {
+      if (c->peers.nranks > 1) c->max_seq += 1;
+      k_conv_fft<K, true><<<grid, C::THREADS, SMEM, c->stream>>>(c->tm_err_fft, c->tm_u_fepi, c->tm_ut_fepi, c->g, c->st, c->wspec,
+                                                               lambd, c->gbuf, ntx, nty, y0, y1, c->peers, c->max_seq, c->counters + 1);
+    } else {
+      k_conv_fft<K, false><<<grid, C::THREADS, SMEM, c->stream>>>(c->tm_u_fft, c->tm_img_fepi, c->tm_img_fepi, c->g, c->st, c->wspec,
+                                                                lambd, c->err, ntx, nty, y0, y1, c->peers, 0, c->counters + 1);
+    }
+    return RLTV_OK;
+  } else {
+    return fail(RLTV_ERR_ARG, "row-FFT stencils exist for 9 <= MK <= 17");
+  }
+}
+
+int launch_psf_spectrum(rltv_ctx* c) {
+  if (!c->use_fft) return RLTV_OK;
+  ProfScope p(c, F_PSF);
+  k_psf_spectrum<<<dim3(c->g.K, 3, 2), FFT_N, 0, c->stream>>>(c->st, c->psf, c->g.K, c->wspec);
   return RLTV_OK;
 }
 
 // forward residual on local rows [fwd0, fwd1); adjoint on the owned rows
 template <int K, bool ADJ>
 int launch_conv_t(rltv_ctx* c, float lambd) {
+  if (c->use_fft) return launch_conv_fft_t<K, ADJ>(c, lambd);
   using C = ConvCfg<K>;
   constexpr int SMEM = C::smem_bytes(ADJ);
   CU(cudaFuncSetAttribute(k_conv<K, ADJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -272,11 +320,13 @@ int launch_update(rltv_ctx* c) {
 
 int launch_psf_update(rltv_ctx* c) {
   const int K = c->g.K;
-  ProfScope p(c, F_PSF);
-  k_psf_update<<<1, 256, 6 * K * K * sizeof(float), c->stream>>>(c->st, c->gk_sum, K, c->params.step_factor,
-                                                                c->params.correlation, c->psf, c->psf_caller,
-                                                                c->peers.peer[c->rank], c->peers.nranks, c->gk_seq);
-  return RLTV_OK;
+  {
+    ProfScope p2(c, F_PSF);
+    k_psf_update<<<1, 256, 6 * K * K * sizeof(float), c->stream>>>(c->st, c->gk_sum, K, c->params.step_factor,
+                                                                  c->params.correlation, c->psf, c->psf_caller,
+                                                                  c->peers.peer[c->rank], c->peers.nranks, c->gk_seq);
+  }
+  return launch_psf_spectrum(c);
 }
 
 int launch_halo_push(rltv_ctx* c) {
@@ -570,6 +620,14 @@ int rltv_create_band(rltv_ctx** out, int32_t device, int32_t M, int32_t N, int32
   c->gk_nparts = c->num_sms;   // persistent k_gradk: one CTA per SM, one partial per CTA
   CU(cudaMalloc(&c->gk_partial, size_t(3) * c->gk_nparts * MK * MK * sizeof(float)));
   CU(cudaMalloc(&c->gk_sum, size_t(3) * MK * MK * sizeof(double)));
+  CU(cudaMalloc(&c->wspec, size_t(2) * 3 * MK * FFT_N * sizeof(float2)));
+  {
+    // Row-FFT hybrid stencils (csrc/rltv_stencil_fft.cuh) for the FP32-bound sizes; RLTV_CONV=direct|fft overrides
+    const char* e = getenv("RLTV_CONV");
+    c->use_fft = false;
+    if (e && !strcmp(e, "direct")) c->use_fft = false;
+    if (e && !strcmp(e, "fft") && MK >= 9 && MK <= 17) c->use_fft = true;
+  }
   {
     int rc = make_maps(c);
     if (rc) { std::string keep = g_err; rltv_destroy(c); g_err = keep; return rc; }
@@ -593,7 +651,7 @@ int rltv_destroy(rltv_ctx* c) {
   for (auto p : f) cudaFree(p);
   double* d[] = {c->gk_sum, c->wa, c->wb, c->rowacc, c->rowsum};
   for (auto p : d) cudaFree(p);
-  cudaFree(c->Z); cudaFree(c->tw); cudaFree(c->st); cudaFree(c->counters);
+  cudaFree(c->Z); cudaFree(c->tw); cudaFree(c->st); cudaFree(c->counters); cudaFree(c->wspec);
   if (c->h_st) cudaFreeHost(c->h_st);
   if (c->h_poll) cudaFreeHost(c->h_poll);
   for (auto& e : c->poll_ev) if (e) cudaEventDestroy(e);
@@ -633,6 +691,11 @@ int rltv_upload_band(rltv_ctx* c, const float* image, size_t image_rs, int32_t i
     k_psf_pack<<<(3 * KK2 + 255) / 256, 256, 0, c->stream>>>(c->psf_hwc, c->psf, KK2, 1);
     CU(cudaMemcpyAsync(c->psf_caller, c->psf, size_t(3) * KK2 * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
     c->launches++;
+    if (c->use_fft) {
+      CU(cudaMemsetAsync(c->st, 0, sizeof(int), c->stream));   // a stop flag left by an earlier solve must not skip this
+      int rc2 = launch_psf_spectrum(c);
+      if (rc2) return rc2;
+    }
   }
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(c->stream));   // the host arrays may be pageable views: do not outlive the call
@@ -974,6 +1037,25 @@ int rltv_stage_tv(rltv_ctx* c, int32_t order, int32_t norm, float epsilon, float
   // the residual buffer was used as scratch: restore its zero ring for the next solve
   CU(cudaMemsetAsync(c->err, 0, 3 * g.plane * sizeof(float), c->stream));
   CU(cudaStreamSynchronize(c->stream));
+  return RLTV_OK;
+}
+
+// Test entry point of the shared-memory FFT engine (csrc/rltv_fft.cuh): nrows x 128 complex (interleaved re,im).
+int rltv_debug_fft128(const float* in, float* out, int32_t nrows, int32_t inverse, int32_t device) {
+  if (!in || !out || nrows < 1) return fail(RLTV_ERR_ARG, "bad arguments");
+  if (rltv_device_count() <= 0) return fail(RLTV_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+  CU(cudaSetDevice(device));
+  float2 *d_in = nullptr, *d_out = nullptr;
+  const size_t bytes = size_t(nrows) * FFT_N * sizeof(float2);
+  CU(cudaMalloc(&d_in, bytes));
+  CU(cudaMalloc(&d_out, bytes));
+  CU(cudaMemcpy(d_in, in, bytes, cudaMemcpyHostToDevice));
+  if (inverse) k_fft128_debug<true><<<(nrows + 15) / 16, 128>>>(d_in, d_out, nrows);
+  else k_fft128_debug<false><<<(nrows + 15) / 16, 128>>>(d_in, d_out, nrows);
+  cudaError_t e = cudaMemcpy(out, d_out, bytes, cudaMemcpyDeviceToHost);
+  cudaFree(d_in);
+  cudaFree(d_out);
+  if (e != cudaSuccess) return fail(RLTV_ERR_CUDA, cudaGetErrorString(e));
   return RLTV_OK;
 }
 

@@ -232,3 +232,63 @@ def test_pyramid_driver_on_gpu_matches_oracle_driven_flow(tmp_path):
     psf_ref = drv.deblur_module.last_psf.copy()
     assert rel_l2(out_gpu, out_ref) <= TOL_IMAGE_REL_L2
     assert psf_l1(psf_gpu, psf_ref) <= TOL_PSF_L1
+
+
+@pytest.mark.parametrize("inverse", [0, 1])
+def test_fft128_engine(inverse):
+    """csrc/rltv_fft.cuh (16 x 8 register passes over shared memory) against numpy's FFT."""
+    import __graft_entry__ as g
+    g.build()
+    from image_cases_studies_b200 import _native as nat
+    rng = np.random.default_rng(3)
+    nrows = 37
+    x = (rng.standard_normal((nrows, 128)) + 1j * rng.standard_normal((nrows, 128))).astype(np.complex64)
+    out = np.empty_like(x)
+    nat.check(nat.lib.rltv_debug_fft128(nat.ptr(x.view(np.float32)), nat.ptr(out.view(np.float32)), nrows, inverse, 0))
+    ref = np.fft.ifft(x.astype(np.complex128), axis=1) * 128 if inverse else np.fft.fft(x.astype(np.complex128), axis=1)
+    assert np.abs(out - ref).max() <= 2e-5 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("K", [9, 11, 13, 15, 17])
+def test_row_fft_stencils_against_oracle(K, monkeypatch):
+    """k_conv_fft (row-FFT hybrid forward blur / adjoint, csrc/rltv_stencil_fft.cuh) against the float64 definition."""
+    from image_cases_studies_b200.solver import Solver
+    from oracle import rl_mm_oracle as orc
+    monkeypatch.setenv("RLTV_CONV", "fft")
+    rng = np.random.default_rng(K)
+    M, N = 150 + 3 * K, 260 + K           # several 64 x 112 tiles, ragged edges
+    u = rng.random((M + K - 1, N + K - 1, 3), dtype=np.float32)
+    image = rng.random((M, N, 3), dtype=np.float32)
+    psf = rng.random((K, K, 3), dtype=np.float32)
+    psf /= psf.sum(axis=(0, 1), keepdims=True)
+    s = Solver(M, N, K)
+    s.upload(image, u, psf)
+    err = s.stage_residual()
+    g = s.stage_adjoint()
+    s.close()
+    for c in range(3):
+        e_ref = orc.conv2(u[..., c], psf[..., c], "valid") - image[..., c]
+        assert rel_l2(err[..., c], e_ref) < 5e-6
+        g_ref = orc.conv2(e_ref, orc.rot180(psf[..., c]), "full")
+        assert rel_l2(g[..., c], g_ref) < 5e-6
+
+
+def test_row_fft_solver_against_oracle(dc, monkeypatch):
+    from image_cases_studies_b200 import synthetic
+    from oracle import rl_mm_oracle as orc
+    monkeypatch.setenv("RLTV_CONV", "fft")
+    dc.clear_cache()
+    try:
+        c = synthetic.make_case("c3_blind_24mp_k15", seed=7, scale=0.06, iterations=3)
+        M, N = c.shape
+        g = dict(image=c.image, u0=c.u0, psf0=c.psf0, window=c.window, tau=c.tau, iterations=c.iterations,
+                 step_factor=c.step_factor, lambd=c.lambd, blind=c.blind, correlation=False)
+        out, u, psf, st = _run_dc(dc, g)
+        ref = orc.richardson_lucy_MM(c.image, c.u0, c.psf0, *c.window, c.tau, M, N, 3, c.MK, c.iterations,
+                                     c.step_factor, c.lambd, blind=c.blind)
+        assert st["iterations"] == ref.iterations
+        assert rel_l2(out, ref.out) <= TOL_IMAGE_REL_L2
+        assert psf_l1(psf, ref.psf) <= TOL_PSF_L1
+        assert np.allclose(st["M_r_history"], ref.M_r, rtol=2e-5)
+    finally:
+        dc.clear_cache()
