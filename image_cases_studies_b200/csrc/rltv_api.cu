@@ -74,8 +74,8 @@ struct rltv_ctx {
   int num_sms = 148;
   // TMA descriptors (rank-3 tensors x: Wu, y: rows, c: 3 over the planar arrays; boxes per kernel)
   CUtensorMap tm_u_conv{}, tm_err_conv{}, tm_img_epi{}, tm_u_epi{}, tm_ut_epi{}, tm_u_gk{}, tm_err_gk{};
-  // row-FFT hybrid stencils (K <= 17): boxes 128 x (64+K-1) for the input, 112 x 64 for the epilogue operands
-  CUtensorMap tm_u_fft{}, tm_err_fft{}, tm_img_fepi{}, tm_u_fepi{}, tm_ut_fepi{};
+  // row-FFT hybrid stencils (9 <= K <= 17): input boxes 128 x (96+K-1)
+  CUtensorMap tm_u_fft{}, tm_err_fft{};
   float2* wspec = nullptr;      // tap spectra [2][3][K][128]
   bool use_fft = false;
   double* gk_sum = nullptr;
@@ -203,9 +203,6 @@ int make_maps_t(rltv_ctx* c) {
     using F = FftCfg<K>;
     if ((rc = make_tmap(&c->tm_u_fft, c->u, g, g.Hu, FFT_N, F::IN_ROWS))) return rc;
     if ((rc = make_tmap(&c->tm_err_fft, c->err, g, g.Hu, FFT_N, F::IN_ROWS))) return rc;
-    if ((rc = make_tmap(&c->tm_img_fepi, c->img, g, g.Hu, F::TWO, F::TROWS))) return rc;
-    if ((rc = make_tmap(&c->tm_u_fepi, c->u, g, g.Hu, F::TWO, F::TROWS))) return rc;
-    if ((rc = make_tmap(&c->tm_ut_fepi, c->ut, g, g.Hu, F::TWO, F::TROWS))) return rc;
   }
   return RLTV_OK;
 }
@@ -214,7 +211,7 @@ template <int K, bool ADJ>
 int launch_conv_fft_t(rltv_ctx* c, float lambd) {
   if constexpr (K >= 9 && K <= 17) {
     using C = FftCfg<K>;
-    constexpr int SMEM = C::smem_bytes(ADJ);
+    constexpr int SMEM = C::SMEM_BYTES;
     CU(cudaFuncSetAttribute(k_conv_fft<K, ADJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     const int y0 = ADJ ? c->g.own0 : c->fwd0, y1 = ADJ ? c->g.own1 : c->fwd1;
     const int ntx = (c->g.Wu + C::TWO - 1) / C::TWO, nty = (y1 - y0 + C::TROWS - 1) / C::TROWS;
@@ -223,10 +220,10 @@ int launch_conv_fft_t(rltv_ctx* c, float lambd) {
     ProfScope p(c, ADJ ? F_CONV_ADJ : F_CONV_FWD);
     if (ADJ) {
       if (c->peers.nranks > 1) c->max_seq += 1;
-      k_conv_fft<K, true><<<grid, C::THREADS, SMEM, c->stream>>>(c->tm_err_fft, c->tm_u_fepi, c->tm_ut_fepi, c->g, c->st, c->wspec,
+      k_conv_fft<K, true><<<grid, C::THREADS, SMEM, c->stream>>>(c->tm_err_fft, c->u, c->ut, c->g, c->st, c->wspec,
                                                                lambd, c->gbuf, ntx, nty, y0, y1, c->peers, c->max_seq, c->counters + 1);
     } else {
-      k_conv_fft<K, false><<<grid, C::THREADS, SMEM, c->stream>>>(c->tm_u_fft, c->tm_img_fepi, c->tm_img_fepi, c->g, c->st, c->wspec,
+      k_conv_fft<K, false><<<grid, C::THREADS, SMEM, c->stream>>>(c->tm_u_fft, c->img, c->img, c->g, c->st, c->wspec,
                                                                 lambd, c->err, ntx, nty, y0, y1, c->peers, 0, c->counters + 1);
     }
     return RLTV_OK;

@@ -116,19 +116,22 @@ __device__ __forceinline__ void fft_fill_twiddles(float2* tw128) {
 
 // Pass A + B of one row for the 8 threads (t = 0..7) that own it.  `load(n)` returns input element n.
 // On return the row buffer `row` (FFT_PITCH complex) holds the spectrum / signal in natural order [0,128).
+// `rot` (0..15) rotates the order in which the 16 stride-8 samples are fetched (x'[j] = x[(j + rot) mod 16]); by the
+// shift theorem that only changes the pass-A twiddle index.  The four rows a warp handles use different `rot`, so
+// their loads from a dense 512-byte-pitch source (the TMA buffer) fall into different banks.
 template <bool INV, typename Load>
 __device__ __forceinline__ void fft128_row(float2* __restrict__ row, const float2* __restrict__ tw128, int t, Load load,
-                                           unsigned mask = 0xffffffffu) {
+                                           unsigned mask = 0xffffffffu, int rot = 0) {
   float2 x[16];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) x[j] = load(t + 8 * j);
-  dft16<INV>(x);
+  for (int j = 0; j < 16; ++j) x[j] = load(t + 8 * ((j + rot) & 15));
+  dft16<INV>(x);                                 // X'[q] = X[q] * w16^(-rot q)   (forward; conjugate for inverse)
   __syncwarp(mask);                              // everyone's loads are done before anyone stores (in-place rows)
 #pragma unroll
   for (int q = 0; q < 16; ++q) {
-    float2 w = tw128[(t * q) & (FFT_N - 1)];
+    float2 w = tw128[(t * q + 8 * rot * q) & (FFT_N - 1)];      // w128^(t q) * w16^(+rot q) undoes the rotation
     if (INV) w.y = -w.y;
-    row[9 * q + t] = (q == 0) ? x[0] : cmulf(x[q], w);
+    row[9 * q + t] = cmulf(x[q], w);
   }
   __syncwarp(mask);
   // pass B: this thread handles q = t and q = t + 8

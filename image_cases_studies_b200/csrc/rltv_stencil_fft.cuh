@@ -6,14 +6,14 @@
 // the y direction stays a direct sum -- but of SPECTRA:   Out^[Y] = sum_ky Wc[ky] (.) In^[Y-P+ky]   -> K complex MACs
 // per (row, bin) = 4K FMAs per 112/128 outputs instead of K*K: 34 instead of 225 FMAs per output at K = 15, plus two
 // 128-point FFTs per row.  Because the taps are real, two image rows ride through the complex FFT as real and
-// imaginary parts (rows Y and Y+32 of a 64-row tile) and come out as the real and imaginary parts of the inverse
+// imaginary parts (rows Y and Y+48 of a 96-row tile) and come out as the real and imaginary parts of the inverse
 // transform: no real-FFT untangling anywhere.
 //
-// Per 64 x 112 output tile (one CTA of 512 threads per SM, persistent, TMA double-buffered input like k_conv):
-//   1. forward FFT of the 32+K-1 packed rows straight out of the TMA buffer          (csrc/rltv_fft.cuh)
-//   2. vertical MAC over spectra: thread = (bin, chunk of 8 output rows), K complex taps in registers
-//   3. inverse FFT of the 32 packed output rows (into the consumed TMA buffer)
-//   4. epilogue identical to k_conv (residual / step statistics), 112 columns x 64 rows
+// Per 96 x 112 output tile (one CTA of 512 threads per SM, persistent, TMA double-buffered input like k_conv):
+//   1. forward FFT of the 48+K-1 packed rows straight out of the TMA buffer          (csrc/rltv_fft.cuh)
+//   2. vertical MAC over spectra: thread = (bin, chunk of 12 output rows), K complex taps in registers
+//   3. inverse FFT of the 48 packed output rows (into the consumed TMA buffer)
+//   4. epilogue as in k_conv (residual / step statistics), 112 columns x 96 rows, operands read from global memory
 #pragma once
 #include "rltv_band.cuh"
 #include "rltv_common.cuh"
@@ -29,21 +29,21 @@ struct FftCfg {
   static constexpr int P = K / 2;
   static constexpr int P4 = (P + 3) & ~3;          // 16-byte aligned TMA box start
   static constexpr int TWO = 112;                  // valid output columns per 128-sample segment
-  static constexpr int HB = 32;                    // rows per packed block (real part: rows 0..31, imaginary: 32..63)
+  static constexpr int HB = 48;                    // rows per packed block (real part: rows 0..47, imaginary: 48..95)
   static constexpr int TROWS = 2 * HB;
   static constexpr int IN_ROWS = TROWS + K - 1;    // TMA box height (real rows)
   static constexpr int ZROWS = HB + K - 1;         // packed complex rows
-  static constexpr int CHUNK = 8;                  // output rows per MAC thread
+  static constexpr int CHUNK = 12;                 // output rows per MAC thread (4 chunks x 128 bins = 512 threads)
   static constexpr int THREADS = 512;
   static constexpr int IN_BYTES = IN_ROWS * FFT_N * 4;                        // TMA transaction size
   static constexpr int ZB_BYTES = ZROWS * FFT_PITCH * 8;
   static constexpr int OB_BYTES = HB * FFT_PITCH * 8;
   static constexpr int STAGE_BYTES = IN_BYTES > OB_BYTES ? IN_BYTES : OB_BYTES;   // the output spectra reuse the stage
-  static constexpr int EPI_BYTES = TROWS * TWO * 4;
   static_assert(P4 + TWO - 1 + P <= FFT_N - 1, "segment too short for this K");
   static_assert(OB_BYTES <= STAGE_BYTES, "output spectra alias the consumed input stage");
-  static_assert(STAGE_BYTES % 128 == 0 && ZB_BYTES % 128 == 0 && EPI_BYTES % 128 == 0, "TMA destinations: 128-byte aligned");
-  static constexpr int smem_bytes(bool adj) { return 2 * STAGE_BYTES + ZB_BYTES + (adj ? 2 : 1) * EPI_BYTES + FFT_N * 8 + 64 + 128; }
+  static_assert(STAGE_BYTES % 128 == 0 && ZB_BYTES % 128 == 0, "TMA destinations: 128-byte aligned");
+  static_assert(4 * CHUNK == HB, "MAC chunks cover the packed rows");
+  static constexpr int SMEM_BYTES = 2 * STAGE_BYTES + ZB_BYTES + FFT_N * 8 + 64 + 128;
 };
 
 // Tap spectra: wspec[dir][c][ky][k] = (1/128) sum_{j=-P..P} w[ky][j+P] exp(+2 pi i j k / 128), w = rot180(psf) for
@@ -66,8 +66,8 @@ k_psf_spectrum(const State* __restrict__ st, const float* __restrict__ psf, int 
 
 template <int K, bool ADJ>
 __global__ void __launch_bounds__(FftCfg<K>::THREADS, 1)
-k_conv_fft(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_e0,
-           const __grid_constant__ CUtensorMap tm_e1, Geom g, State* __restrict__ st, const float2* __restrict__ wspec,
+k_conv_fft(const __grid_constant__ CUtensorMap tm_in, const float* __restrict__ e0g, const float* __restrict__ e1g,
+           Geom g, State* __restrict__ st, const float2* __restrict__ wspec,
            float lambd, float* __restrict__ out, int ntx, int nty, int ybeg, int yend, CommPeers cp, int seq,
            unsigned* __restrict__ done_counter) {
   using C = FftCfg<K>;
@@ -75,9 +75,7 @@ k_conv_fft(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CU
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
   float2* ZB = reinterpret_cast<float2*>(smem + 2 * C::STAGE_BYTES);
-  float* e0 = reinterpret_cast<float*>(smem + 2 * C::STAGE_BYTES + C::ZB_BYTES);
-  float* e1 = reinterpret_cast<float*>(smem + 2 * C::STAGE_BYTES + C::ZB_BYTES + C::EPI_BYTES);
-  float2* tw = reinterpret_cast<float2*>(smem + 2 * C::STAGE_BYTES + C::ZB_BYTES + (ADJ ? 2 : 1) * C::EPI_BYTES);
+  float2* tw = reinterpret_cast<float2*>(smem + 2 * C::STAGE_BYTES + C::ZB_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(tw) + FFT_N * 8);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tiles_per_c = ntx * nty, ntiles = 3 * tiles_per_c;
@@ -89,11 +87,8 @@ k_conv_fft(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CU
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
-    mbar_init(&bars[2], 1);
     fence_mbar_init();
     tma_prefetch_desc(&tm_in);
-    tma_prefetch_desc(&tm_e0);
-    if (ADJ) tma_prefetch_desc(&tm_e1);
   }
   fft_fill_twiddles(tw);
   __syncthreads();
@@ -104,16 +99,8 @@ k_conv_fft(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CU
     mbar_arrive_expect_tx(&bars[s], C::IN_BYTES);
     tma_load_3d(smem + s * C::STAGE_BYTES, &tm_in, bx * C::TWO - C::P4, ybeg + by * C::TROWS - C::P, c, &bars[s]);
   };
-  auto issue_epi = [&](int t) {
-    const int c = t / tiles_per_c, r = t - c * tiles_per_c;
-    const int by = r / ntx, bx = r - by * ntx;
-    mbar_arrive_expect_tx(&bars[2], (ADJ ? 2 : 1) * C::EPI_BYTES);
-    tma_load_3d(e0, &tm_e0, bx * C::TWO, ybeg + by * C::TROWS, c, &bars[2]);
-    if (ADJ) tma_load_3d(e1, &tm_e1, bx * C::TWO, ybeg + by * C::TROWS, c, &bars[2]);
-  };
-
   // MAC role of this thread: frequency bin and chunk of output rows
-  const int bin = tid & (FFT_N - 1), chunk = tid >> 7;          // 4 chunks x 8 rows = 32 packed output rows
+  const int bin = tid & (FFT_N - 1), chunk = tid >> 7;          // 4 chunks x 12 rows = 48 packed output rows
   float2 wreg[K];
 
   int t = blockIdx.x;
@@ -127,7 +114,6 @@ k_conv_fft(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CU
     if (tid == 0) {
       const int tn = t + gridDim.x;
       if (tn < ntiles) issue_in(tn, s ^ 1);
-      issue_epi(t);
     }
     if (c != cur_c) {
       const float2* wsrc = wspec + ((size_t(ADJ ? 1 : 0) * 3 + c) * K) * FFT_N + bin;
@@ -146,7 +132,7 @@ k_conv_fft(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CU
         const int zr = task >> 3, tt = task & 7;
         const float* ra = inR + zr * FFT_N;
         const float* rb = inR + (zr + C::HB) * FFT_N;
-        fft128_row<false>(ZB + zr * FFT_PITCH, tw, tt, [&](int n) { return make_float2(ra[n], rb[n]); }, mask);
+        fft128_row<false>(ZB + zr * FFT_PITCH, tw, tt, [&](int n) { return make_float2(ra[n], rb[n]); }, mask, zr & 3);
       }
     }
     __syncthreads();
@@ -172,7 +158,26 @@ k_conv_fft(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CU
     }
     __syncthreads();
 
-    // 3. inverse FFT of the 32 packed output rows, in place
+    // Epilogue operands of this thread's outputs go to registers now, so their DRAM latency hides behind the
+    // inverse FFT.  Epilogue task = (packed row y, column pair p): outputs (y, 2p..2p+1) and (y + HB, 2p..2p+1).
+    constexpr int NPAIRS = C::TWO / 2, NTASK = (C::HB * NPAIRS + C::THREADS - 1) / C::THREADS;
+    float2 pa[NTASK][2], pb[ADJ ? NTASK : 1][2];
+#pragma unroll
+    for (int q = 0; q < NTASK; ++q) {
+      const int i = tid + q * C::THREADS;
+      const int y = i / NPAIRS, p = i - y * NPAIRS;
+      const int X = bx * C::TWO + 2 * p;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int Y = ybeg + by * C::TROWS + y + h * C::HB;
+        const bool ok = (i < C::HB * NPAIRS) && Y < yend && X < g.pitch;
+        const size_t goff = size_t(c) * g.plane + size_t(ok ? Y : 0) * g.pitch + (ok ? X : 0);
+        pa[q][h] = ok ? __ldg(reinterpret_cast<const float2*>(e0g + goff)) : make_float2(0.f, 0.f);
+        if (ADJ) pb[q][h] = ok ? __ldg(reinterpret_cast<const float2*>(e1g + goff)) : make_float2(0.f, 0.f);
+      }
+    }
+
+    // 3. inverse FFT of the packed output rows, in place
     for (int task = tid; task < C::HB * 8; task += C::THREADS) {
       const unsigned mask = __activemask();
       const int zr = task >> 3, tt = task & 7;
@@ -180,45 +185,48 @@ k_conv_fft(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CU
       fft128_row<true>(row, tw, tt, [&](int n) { return row[n]; }, mask);
     }
     __syncthreads();
-    mbar_wait(&bars[2], k & 1);
 
-    // 4. epilogue: real part -> rows 0..31 of the tile, imaginary part -> rows 32..63; columns P4 .. P4+111 are valid
+    // 4. epilogue: real part -> rows 0..HB-1 of the tile, imaginary part -> rows HB..2HB-1; columns P4 .. P4+111 valid
     {
       float* op = out + size_t(c) * g.plane;
-      for (int i = tid; i < C::TROWS * (C::TWO / 4); i += C::THREADS) {
-        const int row = i / (C::TWO / 4), c4 = i - row * (C::TWO / 4);
-        const int Y = ybeg + by * C::TROWS + row, X = bx * C::TWO + 4 * c4;
-        if (Y >= yend || X >= g.pitch) continue;
-        const float2* src = OB + (row & (C::HB - 1)) * FFT_PITCH + C::P4 + 4 * c4;
-        float v[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = (row < C::HB) ? src[j].x : src[j].y;
-        const float4 a = *reinterpret_cast<const float4*>(e0 + row * C::TWO + 4 * c4);
-        const float av[4] = {a.x, a.y, a.z, a.w};
-        float o[4];
-        if (!ADJ) {
-          const int gy = g.row0 + Y;
-          const bool rowin = (gy >= C::P) && (gy < C::P + g.M);
+      for (int q = 0; q < NTASK; ++q) {
+        const int i = tid + q * C::THREADS;
+        if (i >= C::HB * NPAIRS) break;
+        const int y = i / NPAIRS, p = i - y * NPAIRS;
+        const int X = bx * C::TWO + 2 * p;
+        if (X >= g.pitch) continue;
+        const float4 zz = *reinterpret_cast<const float4*>(OB + y * FFT_PITCH + C::P4 + 2 * p);   // two complex values
+        const float v[2][2] = {{zz.x, zz.z}, {zz.y, zz.w}};                                       // [h][column]
 #pragma unroll
-          for (int j = 0; j < 4; ++j) o[j] = (rowin && (X + j) >= C::P && (X + j) < C::P + g.N) ? v[j] - av[j] : 0.f;
-        } else {
-          const float4 b = *reinterpret_cast<const float4*>(e1 + row * C::TWO + 4 * c4);
-          const float bv[4] = {b.x, b.y, b.z, b.w};
+        for (int h = 0; h < 2; ++h) {
+          const int Y = ybeg + by * C::TROWS + y + h * C::HB;
+          if (Y >= yend) continue;
+          const float av[2] = {pa[q][h].x, pa[q][h].y};
+          float o[2];
+          if (!ADJ) {
+            const int gy = g.row0 + Y;
+            const bool rowin = (gy >= C::P) && (gy < C::P + g.M);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const bool in = (X + j) < g.Wu;
-            o[j] = in ? v[j] : 0.f;
-            if (in && Y >= g.own0 && Y < g.own1) {
-              const float G = fmaf(lambd, v[j], 0.5f * (av[j] - bv[j]));   // pyx:519
-              mu = fmaxf(mu, av[j]);
-              mG = fmaxf(mG, fabsf(G));
+            for (int j = 0; j < 2; ++j) o[j] = (rowin && (X + j) >= C::P && (X + j) < C::P + g.N) ? v[h][j] - av[j] : 0.f;
+          } else {
+            const float bv[2] = {pb[q][h].x, pb[q][h].y};
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const bool in = (X + j) < g.Wu;
+              o[j] = in ? v[h][j] : 0.f;
+              if (in && Y >= g.own0 && Y < g.own1) {
+                const float G = fmaf(lambd, v[h][j], 0.5f * (av[j] - bv[j]));   // pyx:519
+                mu = fmaxf(mu, av[j]);
+                mG = fmaxf(mG, fabsf(G));
+              }
             }
           }
+          *reinterpret_cast<float2*>(op + size_t(Y) * g.pitch + X) = make_float2(o[0], o[1]);
         }
-        *reinterpret_cast<float4*>(op + size_t(Y) * g.pitch + X) = make_float4(o[0], o[1], o[2], o[3]);
       }
     }
-    __syncthreads();   // stage s (now holding O), ZB, e0, e1 are free again
+    __syncthreads();   // stage s (now holding O) and ZB are free again
     if (ADJ) {
       const int tn = t + gridDim.x;
       const int cn = tn < ntiles ? tn / tiles_per_c : -1;
