@@ -123,13 +123,21 @@ template <bool INV, typename Load>
 __device__ __forceinline__ void fft128_row(float2* __restrict__ row, const float2* __restrict__ tw128, int t, Load load,
                                            unsigned mask = 0xffffffffu, int rot = 0) {
   float2 x[16];
+  const int base = t + 8 * rot;                  // rot <= 3: only j >= 13 can wrap around
 #pragma unroll
-  for (int j = 0; j < 16; ++j) x[j] = load(t + 8 * ((j + rot) & 15));
+  for (int j = 0; j < 16; ++j) {
+    int n = base + 8 * j;
+    if (j >= 13 && n >= FFT_N) n -= FFT_N;
+    x[j] = load(n);
+  }
   dft16<INV>(x);                                 // X'[q] = X[q] * w16^(-rot q)   (forward; conjugate for inverse)
   __syncwarp(mask);                              // everyone's loads are done before anyone stores (in-place rows)
+  row[t] = x[0];
+  int widx = 0;
 #pragma unroll
-  for (int q = 0; q < 16; ++q) {
-    float2 w = tw128[(t * q + 8 * rot * q) & (FFT_N - 1)];      // w128^(t q) * w16^(+rot q) undoes the rotation
+  for (int q = 1; q < 16; ++q) {
+    widx = (widx + base) & (FFT_N - 1);          // (t + 8 rot) q mod 128: w128^(t q) * w16^(+rot q) undoes the rotation
+    float2 w = tw128[widx];
     if (INV) w.y = -w.y;
     row[9 * q + t] = cmulf(x[q], w);
   }

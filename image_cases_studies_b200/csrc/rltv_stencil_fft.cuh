@@ -42,7 +42,7 @@ struct FftCfg {
   static_assert(P4 + TWO - 1 + P <= FFT_N - 1, "segment too short for this K");
   static_assert(OB_BYTES <= STAGE_BYTES, "output spectra alias the consumed input stage");
   static_assert(STAGE_BYTES % 128 == 0 && ZB_BYTES % 128 == 0, "TMA destinations: 128-byte aligned");
-  static_assert(4 * CHUNK == HB, "MAC chunks cover the packed rows");
+  static_assert(4 * CHUNK == HB && HB % 8 == 0, "MAC chunks / epilogue row slots cover the packed rows");
   static constexpr int SMEM_BYTES = 2 * STAGE_BYTES + ZB_BYTES + FFT_N * 8 + 64 + 128;
 };
 
@@ -102,6 +102,9 @@ k_conv_fft(const __grid_constant__ CUtensorMap tm_in, const float* __restrict__ 
   // MAC role of this thread: frequency bin and chunk of output rows
   const int bin = tid & (FFT_N - 1), chunk = tid >> 7;          // 4 chunks x 12 rows = 48 packed output rows
   float2 wreg[K];
+  // epilogue role: 8 row slots x 56 column pairs = 448 of the 512 threads
+  const int er = tid / (C::TWO / 2), ep = tid - er * (C::TWO / 2);
+  const bool epi_active = er < 8;
 
   int t = blockIdx.x;
   if (tid == 0 && t < ntiles) issue_in(t, 0);
@@ -159,23 +162,22 @@ k_conv_fft(const __grid_constant__ CUtensorMap tm_in, const float* __restrict__ 
     __syncthreads();
 
     // Epilogue operands of this thread's outputs go to registers now, so their DRAM latency hides behind the
-    // inverse FFT.  Epilogue task = (packed row y, column pair p): outputs (y, 2p..2p+1) and (y + HB, 2p..2p+1).
-    constexpr int NPAIRS = C::TWO / 2, NTASK = (C::HB * NPAIRS + C::THREADS - 1) / C::THREADS;
+    // inverse FFT.  Epilogue thread = (row slot er of 8, column pair ep of 56): outputs (er + 8q [+ HB], 2ep..2ep+1).
+    constexpr int NTASK = C::HB / 8;
+    const int X = bx * C::TWO + 2 * ep;
+    const int Ybase = ybeg + by * C::TROWS + er;
+    const bool xok = epi_active && X < g.pitch;
+    const size_t off0 = size_t(c) * g.plane + size_t(Ybase) * g.pitch + X;
     float2 pa[NTASK][2], pb[ADJ ? NTASK : 1][2];
 #pragma unroll
-    for (int q = 0; q < NTASK; ++q) {
-      const int i = tid + q * C::THREADS;
-      const int y = i / NPAIRS, p = i - y * NPAIRS;
-      const int X = bx * C::TWO + 2 * p;
+    for (int q = 0; q < NTASK; ++q)
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        const int Y = ybeg + by * C::TROWS + y + h * C::HB;
-        const bool ok = (i < C::HB * NPAIRS) && Y < yend && X < g.pitch;
-        const size_t goff = size_t(c) * g.plane + size_t(ok ? Y : 0) * g.pitch + (ok ? X : 0);
+        const bool ok = xok && (Ybase + 8 * q + h * C::HB) < yend;
+        const size_t goff = ok ? off0 + size_t(8 * q + h * C::HB) * g.pitch : 0;
         pa[q][h] = ok ? __ldg(reinterpret_cast<const float2*>(e0g + goff)) : make_float2(0.f, 0.f);
         if (ADJ) pb[q][h] = ok ? __ldg(reinterpret_cast<const float2*>(e1g + goff)) : make_float2(0.f, 0.f);
       }
-    }
 
     // 3. inverse FFT of the packed output rows, in place
     for (int task = tid; task < C::HB * 8; task += C::THREADS) {
@@ -187,20 +189,17 @@ k_conv_fft(const __grid_constant__ CUtensorMap tm_in, const float* __restrict__ 
     __syncthreads();
 
     // 4. epilogue: real part -> rows 0..HB-1 of the tile, imaginary part -> rows HB..2HB-1; columns P4 .. P4+111 valid
-    {
-      float* op = out + size_t(c) * g.plane;
+    if (xok) {
+      float* op = out + off0;
+      const bool cin[2] = {ADJ ? (X < g.Wu) : (X >= C::P && X < C::P + g.N),
+                           ADJ ? (X + 1 < g.Wu) : (X + 1 >= C::P && X + 1 < C::P + g.N)};
 #pragma unroll
       for (int q = 0; q < NTASK; ++q) {
-        const int i = tid + q * C::THREADS;
-        if (i >= C::HB * NPAIRS) break;
-        const int y = i / NPAIRS, p = i - y * NPAIRS;
-        const int X = bx * C::TWO + 2 * p;
-        if (X >= g.pitch) continue;
-        const float4 zz = *reinterpret_cast<const float4*>(OB + y * FFT_PITCH + C::P4 + 2 * p);   // two complex values
-        const float v[2][2] = {{zz.x, zz.z}, {zz.y, zz.w}};                                       // [h][column]
+        const float4 zz = *reinterpret_cast<const float4*>(OB + (er + 8 * q) * FFT_PITCH + C::P4 + 2 * ep);   // 2 complex
+        const float v[2][2] = {{zz.x, zz.z}, {zz.y, zz.w}};                                                   // [h][column]
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const int Y = ybeg + by * C::TROWS + y + h * C::HB;
+          const int Y = Ybase + 8 * q + h * C::HB;
           if (Y >= yend) continue;
           const float av[2] = {pa[q][h].x, pa[q][h].y};
           float o[2];
@@ -208,21 +207,21 @@ k_conv_fft(const __grid_constant__ CUtensorMap tm_in, const float* __restrict__ 
             const int gy = g.row0 + Y;
             const bool rowin = (gy >= C::P) && (gy < C::P + g.M);
 #pragma unroll
-            for (int j = 0; j < 2; ++j) o[j] = (rowin && (X + j) >= C::P && (X + j) < C::P + g.N) ? v[h][j] - av[j] : 0.f;
+            for (int j = 0; j < 2; ++j) o[j] = (rowin && cin[j]) ? v[h][j] - av[j] : 0.f;
           } else {
             const float bv[2] = {pb[q][h].x, pb[q][h].y};
+            const bool owned = Y >= g.own0 && Y < g.own1;
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-              const bool in = (X + j) < g.Wu;
-              o[j] = in ? v[h][j] : 0.f;
-              if (in && Y >= g.own0 && Y < g.own1) {
+              o[j] = cin[j] ? v[h][j] : 0.f;
+              if (cin[j] && owned) {
                 const float G = fmaf(lambd, v[h][j], 0.5f * (av[j] - bv[j]));   // pyx:519
                 mu = fmaxf(mu, av[j]);
                 mG = fmaxf(mG, fabsf(G));
               }
             }
           }
-          *reinterpret_cast<float2*>(op + size_t(Y) * g.pitch + X) = make_float2(o[0], o[1]);
+          *reinterpret_cast<float2*>(op + size_t(8 * q + h * C::HB) * g.pitch) = make_float2(o[0], o[1]);
         }
       }
     }
