@@ -75,7 +75,10 @@ struct rltv_ctx {
   // TMA descriptors (rank-3 tensors x: Wu, y: rows, c: 3 over the planar arrays; boxes per kernel)
   CUtensorMap tm_u_conv{}, tm_err_conv{}, tm_img_epi{}, tm_u_epi{}, tm_ut_epi{}, tm_u_gk{}, tm_err_gk{};
   // row-FFT hybrid stencils (9 <= K <= 17): input boxes 128 x (96+K-1)
-  CUtensorMap tm_u_fft{}, tm_err_fft{};
+  CUtensorMap tm_u_fft{}, tm_err_fft{}, tm_u_gkfft{}, tm_err_gkfft{};
+  float2* gkf_part = nullptr;   // k_gradk_fft: per-CTA frequency-domain sums
+  double2* gkf_gpart = nullptr; // per-group sums + final scratch
+  unsigned* gkf_tickets = nullptr;
   float2* wspec = nullptr;      // tap spectra [2][3][K][128]
   bool use_fft = false;
   double* gk_sum = nullptr;
@@ -203,6 +206,9 @@ int make_maps_t(rltv_ctx* c) {
     using F = FftCfg<K>;
     if ((rc = make_tmap(&c->tm_u_fft, c->u, g, g.Hu, FFT_N, F::IN_ROWS))) return rc;
     if ((rc = make_tmap(&c->tm_err_fft, c->err, g, g.Hu, FFT_N, F::IN_ROWS))) return rc;
+    using GF = GradkFftCfg<K>;
+    if ((rc = make_tmap(&c->tm_u_gkfft, c->u, g, g.Hu, FFT_N, GF::U_ROWS))) return rc;
+    if ((rc = make_tmap(&c->tm_err_gkfft, c->err + size_t(g.own0) * g.pitch, g, g.own1 - g.own0, FFT_N, GF::TROWS))) return rc;
   }
   return RLTV_OK;
 }
@@ -263,7 +269,25 @@ int launch_conv_t(rltv_ctx* c, float lambd) {
 }
 
 template <int K>
+int launch_gradk_fft_t(rltv_ctx* c) {
+  if constexpr (K >= 9 && K <= 17) {
+    using C = GradkFftCfg<K>;
+    CU(cudaFuncSetAttribute(k_gradk_fft<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    const int ntx = (c->g.Wu + C::TWO - 1) / C::TWO, nty = (c->g.own1 - c->g.own0 + C::TROWS - 1) / C::TROWS;
+    if (c->peers.nranks > 1) c->gk_seq += 1;
+    ProfScope p(c, F_GRADK);
+    k_gradk_fft<K><<<c->gk_nparts, C::THREADS, C::SMEM_BYTES, c->stream>>>(c->tm_u_gkfft, c->tm_err_gkfft, c->g, c->st, c->gkf_part,
+                                                                         c->gkf_gpart, c->gkf_tickets, ntx, nty, c->gk_sum,
+                                                                         c->peers, c->gk_seq);
+    return RLTV_OK;
+  } else {
+    return fail(RLTV_ERR_ARG, "row-FFT stencils exist for 9 <= MK <= 17");
+  }
+}
+
+template <int K>
 int launch_gradk_t(rltv_ctx* c) {
+  if (c->use_fft) return launch_gradk_fft_t<K>(c);
   using C = GradkCfg<K>;
   CU(cudaFuncSetAttribute(k_gradk<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   const int ntx = (c->g.Wu + C::TW - 1) / C::TW, nty = (c->g.own1 - c->g.own0 + C::TH - 1) / C::TH;
@@ -619,9 +643,16 @@ int rltv_create_band(rltv_ctx** out, int32_t device, int32_t M, int32_t N, int32
   CU(cudaMalloc(&c->gk_sum, size_t(3) * MK * MK * sizeof(double)));
   CU(cudaMalloc(&c->wspec, size_t(2) * 3 * MK * FFT_N * sizeof(float2)));
   {
+    const int ngroups = (c->gk_nparts + 15) / 16;
+    CU(cudaMalloc(&c->gkf_part, size_t(c->gk_nparts) * 3 * MK * FFT_N * sizeof(float2)));
+    CU(cudaMalloc(&c->gkf_gpart, size_t(ngroups + 1) * 3 * MK * FFT_N * sizeof(double2)));
+    CU(cudaMalloc(&c->gkf_tickets, size_t(ngroups + 1) * sizeof(unsigned)));
+    CU(cudaMemsetAsync(c->gkf_tickets, 0, size_t(ngroups + 1) * sizeof(unsigned), c->stream));
+  }
+  {
     // Row-FFT hybrid stencils (csrc/rltv_stencil_fft.cuh) for the FP32-bound sizes; RLTV_CONV=direct|fft overrides
     const char* e = getenv("RLTV_CONV");
-    c->use_fft = false;
+    c->use_fft = (MK >= 11 && MK <= 17);
     if (e && !strcmp(e, "direct")) c->use_fft = false;
     if (e && !strcmp(e, "fft") && MK >= 9 && MK <= 17) c->use_fft = true;
   }
@@ -648,7 +679,7 @@ int rltv_destroy(rltv_ctx* c) {
   for (auto p : f) cudaFree(p);
   double* d[] = {c->gk_sum, c->wa, c->wb, c->rowacc, c->rowsum};
   for (auto p : d) cudaFree(p);
-  cudaFree(c->Z); cudaFree(c->tw); cudaFree(c->st); cudaFree(c->counters); cudaFree(c->wspec);
+  cudaFree(c->Z); cudaFree(c->tw); cudaFree(c->st); cudaFree(c->counters); cudaFree(c->wspec); cudaFree(c->gkf_part); cudaFree(c->gkf_gpart); cudaFree(c->gkf_tickets);
   if (c->h_st) cudaFreeHost(c->h_st);
   if (c->h_poll) cudaFreeHost(c->h_poll);
   for (auto& e : c->poll_ev) if (e) cudaEventDestroy(e);

@@ -264,3 +264,227 @@ k_conv_fft(const __grid_constant__ CUtensorMap tm_in, const float* __restrict__ 
 }
 
 }  // namespace rltv
+
+namespace rltv {
+
+// ------------------------------------------------------------------------------------------------
+// PSF gradient in the row-frequency domain (lib/deconvolution.pyx:567-571).
+//   gk'[dy][dx] = sum_{Y,X} err[Y][X] u[Y-P+dy][X-P+dx]   is, along x, a cross-correlation:  for one row pair
+//   R[s] = sum_n e[n] u[n+s]  <=>  R^ = conj(E^) U^ .  The K displacement rows dy stay a direct loop, the K lags
+//   dx = s + P come out of ONE inverse transform at the very end, because the products are ACCUMULATED in the
+//   frequency domain over all rows and all tiles:   C[dy][k] += conj(Ze[y][k]) Zu[y+dy][k].
+//   Rows are packed in pairs like in k_conv_fft (Z = row y + i row y+HB); the packed product equals A + iB with
+//   A = conj(E)U + conj(E')U' (wanted) and B a cross term; both are spectra of real sequences, hence
+//   A[k] = (C[k] + conj(C[-k])) / 2 -- untangled once, by the last CTA, before a 15-lag inverse DFT in double.
+// Per 80 x 112 tile: 94 forward row FFTs + 40*128*K complex MACs; no inverse FFT, no epilogue.
+// One real-data stage only: the next tile's TMA is issued as soon as the forward FFTs have consumed the stage and
+// overlaps the MAC phase.
+// ------------------------------------------------------------------------------------------------
+template <int K>
+struct GradkFftCfg {
+  static_assert(K >= 9 && K <= 17, "see FftCfg");
+  static constexpr int P = K / 2;
+  static constexpr int P4 = (P + 3) & ~3;
+  static constexpr int TWO = 112;
+  static constexpr int HB = 40;
+  static constexpr int TROWS = 2 * HB;
+  static constexpr int U_ROWS = TROWS + K - 1;      // real u rows per tile
+  static constexpr int ZU_ROWS = HB + K - 1;
+  static constexpr int CHUNK = HB / 4;
+  static constexpr int THREADS = 512;
+  static constexpr int U_BYTES = U_ROWS * FFT_N * 4;
+  static constexpr int E_BYTES = TROWS * FFT_N * 4;
+  static constexpr int ZU_BYTES = ZU_ROWS * FFT_PITCH * 8;
+  static constexpr int ZE_BYTES = HB * FFT_PITCH * 8;
+  static constexpr int SMEM_BYTES = U_BYTES + E_BYTES + ZU_BYTES + ZE_BYTES + FFT_N * 8 + 64 + 128;
+  static_assert(U_BYTES % 128 == 0 && E_BYTES % 128 == 0 && ZU_BYTES % 128 == 0 && ZE_BYTES % 128 == 0, "alignment");
+  static_assert(SMEM_BYTES <= 227 * 1024, "does not fit shared memory");
+  static constexpr int GROUP = 16;                  // CTAs per first-level reduction group
+};
+
+// part   : [cta][c][dy][k] float2   per-CTA frequency-domain sums
+// gpart  : [group][c][dy][k] double2
+// tickets: [0 .. ngroups-1] per-group counters, [ngroups] final counter
+template <int K>
+__global__ void __launch_bounds__(GradkFftCfg<K>::THREADS, 1)
+k_gradk_fft(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_e, Geom g,
+            const State* __restrict__ st, float2* __restrict__ part, double2* __restrict__ gpart,
+            unsigned* __restrict__ tickets, int ntx, int nty, double* __restrict__ gk_sum, CommPeers cp, int seq) {
+  using C = GradkFftCfg<K>;
+  if (st->stop) return;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+  const float* uR = reinterpret_cast<const float*>(smem);
+  const float* eR = reinterpret_cast<const float*>(smem + C::U_BYTES);
+  float2* ZU = reinterpret_cast<float2*>(smem + C::U_BYTES + C::E_BYTES);
+  float2* ZE = reinterpret_cast<float2*>(smem + C::U_BYTES + C::E_BYTES + C::ZU_BYTES);
+  float2* tw = reinterpret_cast<float2*>(smem + C::U_BYTES + C::E_BYTES + C::ZU_BYTES + C::ZE_BYTES);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(tw) + FFT_N * 8);
+  const int tid = threadIdx.x;
+  const int tiles_per_c = ntx * nty;
+  const int my_tiles = (tiles_per_c > int(blockIdx.x)) ? (tiles_per_c - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x) : 0;
+  const int total = 3 * my_tiles;
+
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&tm_u);
+    tma_prefetch_desc(&tm_e);
+  }
+  fft_fill_twiddles(tw);
+  __syncthreads();
+
+  auto issue = [&](int q) {
+    const int c = q / my_tiles, tl = blockIdx.x + (q - c * my_tiles) * gridDim.x;
+    const int by = tl / ntx, bx = tl - by * ntx;
+    mbar_arrive_expect_tx(bar, C::U_BYTES + C::E_BYTES);
+    tma_load_3d(smem, &tm_u, bx * C::TWO - C::P4, g.own0 + by * C::TROWS - C::P, c, bar);
+    tma_load_3d(smem + C::U_BYTES, &tm_e, bx * C::TWO - C::P4, by * C::TROWS, c, bar);   // tm_e: owned rows only
+  };
+
+  const int bin = tid & (FFT_N - 1), chunk = tid >> 7;
+  float2 acc[K];
+#pragma unroll
+  for (int d = 0; d < K; ++d) acc[d] = make_float2(0.f, 0.f);
+
+  if (tid == 0 && total > 0) issue(0);
+  for (int q = 0; q < total; ++q) {
+    mbar_wait(bar, q & 1);
+    __syncwarp();
+    // forward FFTs: packed u rows, then packed err rows (columns outside the 112 valid ones are zeroed)
+    for (int task = tid; task < (C::ZU_ROWS + C::HB) * 8; task += C::THREADS) {
+      const unsigned mask = __activemask();
+      const int zr = task >> 3, tt = task & 7;
+      if (zr < C::ZU_ROWS) {
+        const float* ra = uR + zr * FFT_N;
+        const float* rb = uR + (zr + C::HB) * FFT_N;
+        fft128_row<false>(ZU + zr * FFT_PITCH, tw, tt, [&](int n) { return make_float2(ra[n], rb[n]); }, mask, zr & 3);
+      } else {
+        const int er = zr - C::ZU_ROWS;
+        const float* ra = eR + er * FFT_N;
+        const float* rb = eR + (er + C::HB) * FFT_N;
+        fft128_row<false>(ZE + er * FFT_PITCH, tw, tt, [&](int n) {
+          const bool in = (n >= C::P4) && (n < C::P4 + C::TWO);
+          return in ? make_float2(ra[n], rb[n]) : make_float2(0.f, 0.f);
+        }, mask, zr & 3);
+      }
+    }
+    __syncthreads();
+    if (tid == 0 && q + 1 < total) issue(q + 1);      // the real-data stage is free: overlap the load with the MAC
+    // MAC: C[dy][bin] += conj(Ze[y][bin]) * Zu[y + dy][bin]
+    {
+      float2 zu[C::CHUNK + K - 1];
+#pragma unroll
+      for (int i = 0; i < C::CHUNK + K - 1; ++i) zu[i] = ZU[(chunk * C::CHUNK + i) * FFT_PITCH + bin];
+#pragma unroll
+      for (int y = 0; y < C::CHUNK; ++y) {
+        const float2 e = ZE[(chunk * C::CHUNK + y) * FFT_PITCH + bin];
+#pragma unroll
+        for (int d = 0; d < K; ++d) {
+          acc[d].x = fmaf(e.x, zu[y + d].x, acc[d].x);
+          acc[d].x = fmaf(e.y, zu[y + d].y, acc[d].x);
+          acc[d].y = fmaf(e.x, zu[y + d].y, acc[d].y);
+          acc[d].y = fmaf(-e.y, zu[y + d].x, acc[d].y);
+        }
+      }
+    }
+    __syncthreads();      // ZU / ZE are free for the next tile
+    const int c = q / my_tiles;
+    if (q + 1 == total || (q + 1) / my_tiles != c) {
+      // end of a channel: fold the 4 row chunks (fixed order) through ZU and write this CTA's partial
+      float2* red = ZU;   // [chunk][K][128]
+#pragma unroll
+      for (int d = 0; d < K; ++d) {
+        red[(chunk * K + d) * FFT_N + bin] = acc[d];
+        acc[d] = make_float2(0.f, 0.f);
+      }
+      __syncthreads();
+      for (int o = tid; o < K * FFT_N; o += C::THREADS) {
+        float2 s0 = red[o];
+#pragma unroll
+        for (int ch = 1; ch < 4; ++ch) {
+          const float2 v = red[ch * K * FFT_N + o];
+          s0.x += v.x;
+          s0.y += v.y;
+        }
+        part[(size_t(blockIdx.x) * 3 + c) * K * FFT_N + o] = s0;
+      }
+      __syncthreads();
+    }
+  }
+  if (total == 0)
+    for (int o = tid; o < 3 * K * FFT_N; o += C::THREADS) part[size_t(blockIdx.x) * 3 * K * FFT_N + o] = make_float2(0.f, 0.f);
+
+  // ---- deterministic two-level reduction over CTAs (whoever arrives last does the fixed-order sum) ----
+  __shared__ bool last;
+  const int ngroups = (gridDim.x + C::GROUP - 1) / C::GROUP;
+  const int grp = blockIdx.x / C::GROUP;
+  const int g0 = grp * C::GROUP, g1 = min(int(gridDim.x), g0 + C::GROUP);
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) last = (atomicAdd(&tickets[grp], 1u) == unsigned(g1 - g0 - 1));
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  for (int o = tid; o < 3 * K * FFT_N; o += C::THREADS) {
+    double sx = 0.0, sy = 0.0;
+    for (int b = g0; b < g1; ++b) {
+      const float2 v = __ldcg(part + size_t(b) * 3 * K * FFT_N + o);
+      sx += double(v.x);
+      sy += double(v.y);
+    }
+    gpart[size_t(grp) * 3 * K * FFT_N + o] = make_double2(sx, sy);
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    tickets[grp] = 0u;
+    last = (atomicAdd(&tickets[ngroups], 1u) == unsigned(ngroups - 1));
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  // final: sum the groups in order, untangle A[k] = (C[k] + conj(C[-k]))/2, inverse DFT at the K lags s = dx - P
+  double2* tot = gpart + size_t(ngroups) * 3 * K * FFT_N;      // scratch behind the group partials
+  for (int o = tid; o < 3 * K * FFT_N; o += C::THREADS) {
+    double sx = 0.0, sy = 0.0;
+    for (int gi = 0; gi < ngroups; ++gi) {
+      const double2 v = __ldcg(gpart + size_t(gi) * 3 * K * FFT_N + o);
+      sx += v.x;
+      sy += v.y;
+    }
+    tot[o] = make_double2(sx, sy);
+  }
+  __threadfence();
+  __syncthreads();
+  const int par = seq & 1;
+  for (int o = tid; o < 3 * K * K; o += C::THREADS) {
+    const int c = o / (K * K), r = o - c * K * K;
+    const int dy = r / K, dx = r - dy * K;
+    const int s = dx - C::P;
+    const double2* row = tot + (size_t(c) * K + dy) * FFT_N;
+    double sum = 0.0;
+    for (int k = 0; k < FFT_N; ++k) {
+      const double2 a = row[k], b = row[(FFT_N - k) & (FFT_N - 1)];
+      const double ar = 0.5 * (a.x + b.x), ai = 0.5 * (a.y - b.y);      // A[k]
+      double sn, cs;
+      sincospi(2.0 * double((k * s) & (FFT_N - 1)) / double(FFT_N), &sn, &cs);
+      sum += ar * cs - ai * sn;                                           // Re(A[k] e^{+2 pi i k s / N})
+    }
+    sum *= 1.0 / double(FFT_N);
+    gk_sum[o] = sum;
+    if (cp.nranks > 1)
+      for (int rr = 0; rr < cp.nranks; ++rr) cp.peer[rr]->gk_val[par][cp.rank][o] = sum;
+  }
+  if (cp.nranks > 1) __threadfence_system();
+  __syncthreads();
+  if (tid == 0) {
+    tickets[ngroups] = 0u;
+    if (cp.nranks > 1) {
+      for (int rr = 0; rr < cp.nranks; ++rr) *reinterpret_cast<volatile int*>(&cp.peer[rr]->gk_flag[par][cp.rank]) = seq;
+      __threadfence_system();
+    }
+  }
+}
+
+}  // namespace rltv
