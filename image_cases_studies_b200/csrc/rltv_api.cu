@@ -1068,6 +1068,17 @@ int rltv_stage_tv(rltv_ctx* c, int32_t order, int32_t norm, float epsilon, float
   return RLTV_OK;
 }
 
+// Debug: per-phase cycle totals of k_conv_fft since the last call (thread 0 of every CTA), then reset.
+int rltv_debug_phase_cycles(uint64_t* out8) {
+  unsigned long long h[8] = {0};
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpyFromSymbol(h, g_fft_phase_cycles, sizeof(h)));
+  unsigned long long z[8] = {0};
+  CU(cudaMemcpyToSymbol(g_fft_phase_cycles, z, sizeof(z)));
+  for (int i = 0; i < 8; ++i) out8[i] = h[i];
+  return RLTV_OK;
+}
+
 // Test entry point of the shared-memory FFT engine (csrc/rltv_fft.cuh): nrows x 128 complex (interleaved re,im).
 int rltv_debug_fft128(const float* in, float* out, int32_t nrows, int32_t inverse, int32_t device) {
   if (!in || !out || nrows < 1) return fail(RLTV_ERR_ARG, "bad arguments");

@@ -64,6 +64,10 @@ k_psf_spectrum(const State* __restrict__ st, const float* __restrict__ psf, int 
   wspec[((size_t(dir) * 3 + c) * K + ky) * FFT_N + k] = make_float2(re * (1.f / FFT_N), im * (1.f / FFT_N));
 }
 
+// Per-phase cycle counters of k_conv_fft (thread 0 of every CTA; read by rltv_debug_phase_cycles): 0 wait for the
+// TMA tile, 1 forward FFT, 2 MAC (+ operand prefetch), 3 inverse FFT, 4 epilogue, 5 statistics flush.
+__device__ unsigned long long g_fft_phase_cycles[8];
+
 template <int K, bool ADJ>
 __global__ void __launch_bounds__(FftCfg<K>::THREADS, 1)
 k_conv_fft(const __grid_constant__ CUtensorMap tm_in, const float* __restrict__ e0g, const float* __restrict__ e1g,
@@ -110,6 +114,8 @@ k_conv_fft(const __grid_constant__ CUtensorMap tm_in, const float* __restrict__ 
   if (tid == 0 && t < ntiles) issue_in(t, 0);
   int cur_c = -1;
   float mu = -INFINITY, mG = 0.f;
+  long long ph[6] = {0, 0, 0, 0, 0, 0}, tprev = clock64();
+  auto mark = [&](int i) { if (tid == 0) { const long long now = clock64(); ph[i] += now - tprev; tprev = now; } };
   for (int k = 0; t < ntiles; ++k, t += gridDim.x) {
     const int s = k & 1;
     const int c = t / tiles_per_c, r = t - c * tiles_per_c;
@@ -125,6 +131,7 @@ k_conv_fft(const __grid_constant__ CUtensorMap tm_in, const float* __restrict__ 
       cur_c = c;
     }
     mbar_wait(&bars[s], (k >> 1) & 1);
+    mark(0);
 
     __syncwarp();
     // 1. forward FFT of the packed rows: Z[r] = in[r] + i in[r + HB], read straight from the TMA buffer
@@ -139,6 +146,7 @@ k_conv_fft(const __grid_constant__ CUtensorMap tm_in, const float* __restrict__ 
       }
     }
     __syncthreads();
+    mark(1);
 
     // 2. vertical MAC over spectra: O[y][bin] = sum_ky Wc[ky][bin] * Z[y + ky][bin]; O overwrites the consumed stage
     float2* OB = reinterpret_cast<float2*>(smem + s * C::STAGE_BYTES);
@@ -179,6 +187,7 @@ k_conv_fft(const __grid_constant__ CUtensorMap tm_in, const float* __restrict__ 
         if (ADJ) pb[q][h] = ok ? __ldg(reinterpret_cast<const float2*>(e1g + goff)) : make_float2(0.f, 0.f);
       }
 
+    mark(2);
     // 3. inverse FFT of the packed output rows, in place
     for (int task = tid; task < C::HB * 8; task += C::THREADS) {
       const unsigned mask = __activemask();
@@ -187,45 +196,76 @@ k_conv_fft(const __grid_constant__ CUtensorMap tm_in, const float* __restrict__ 
       fft128_row<true>(row, tw, tt, [&](int n) { return row[n]; }, mask);
     }
     __syncthreads();
+    mark(3);
 
     // 4. epilogue: real part -> rows 0..HB-1 of the tile, imaginary part -> rows HB..2HB-1; columns P4 .. P4+111 valid
-    if (xok) {
+    {
+      // tile-uniform fast path: every output of the tile is inside the image (forward) / owned and inside u (adjoint)
+      const int Yt = ybeg + by * C::TROWS, Xt = bx * C::TWO;
+      const bool interior = ADJ ? (Xt + C::TWO <= g.Wu && Yt >= g.own0 && Yt + C::TROWS <= g.own1 && Yt + C::TROWS <= yend)
+                                : (Xt >= C::P && Xt + C::TWO <= C::P + g.N && g.row0 + Yt >= C::P &&
+                                   g.row0 + Yt + C::TROWS <= C::P + g.M && Yt + C::TROWS <= yend);
       float* op = out + off0;
-      const bool cin[2] = {ADJ ? (X < g.Wu) : (X >= C::P && X < C::P + g.N),
-                           ADJ ? (X + 1 < g.Wu) : (X + 1 >= C::P && X + 1 < C::P + g.N)};
+      if (interior) {
+        if (epi_active) {
 #pragma unroll
-      for (int q = 0; q < NTASK; ++q) {
-        const float4 zz = *reinterpret_cast<const float4*>(OB + (er + 8 * q) * FFT_PITCH + C::P4 + 2 * ep);   // 2 complex
-        const float v[2][2] = {{zz.x, zz.z}, {zz.y, zz.w}};                                                   // [h][column]
+          for (int q = 0; q < NTASK; ++q) {
+            const float4 zz = *reinterpret_cast<const float4*>(OB + (er + 8 * q) * FFT_PITCH + C::P4 + 2 * ep);
+            const float v[2][2] = {{zz.x, zz.z}, {zz.y, zz.w}};
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int Y = Ybase + 8 * q + h * C::HB;
-          if (Y >= yend) continue;
-          const float av[2] = {pa[q][h].x, pa[q][h].y};
-          float o[2];
-          if (!ADJ) {
-            const int gy = g.row0 + Y;
-            const bool rowin = (gy >= C::P) && (gy < C::P + g.M);
-#pragma unroll
-            for (int j = 0; j < 2; ++j) o[j] = (rowin && cin[j]) ? v[h][j] - av[j] : 0.f;
-          } else {
-            const float bv[2] = {pb[q][h].x, pb[q][h].y};
-            const bool owned = Y >= g.own0 && Y < g.own1;
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              o[j] = cin[j] ? v[h][j] : 0.f;
-              if (cin[j] && owned) {
-                const float G = fmaf(lambd, v[h][j], 0.5f * (av[j] - bv[j]));   // pyx:519
-                mu = fmaxf(mu, av[j]);
-                mG = fmaxf(mG, fabsf(G));
+            for (int h = 0; h < 2; ++h) {
+              float2 o;
+              if (!ADJ) {
+                o = make_float2(v[h][0] - pa[q][h].x, v[h][1] - pa[q][h].y);
+              } else {
+                o = make_float2(v[h][0], v[h][1]);
+                const float G0 = fmaf(lambd, o.x, 0.5f * (pa[q][h].x - pb[q][h].x));   // pyx:519
+                const float G1 = fmaf(lambd, o.y, 0.5f * (pa[q][h].y - pb[q][h].y));
+                mu = fmaxf(mu, fmaxf(pa[q][h].x, pa[q][h].y));
+                mG = fmaxf(mG, fmaxf(fabsf(G0), fabsf(G1)));
               }
+              *reinterpret_cast<float2*>(op + size_t(8 * q + h * C::HB) * g.pitch) = o;
             }
           }
-          *reinterpret_cast<float2*>(op + size_t(8 * q + h * C::HB) * g.pitch) = make_float2(o[0], o[1]);
+        }
+      } else if (xok) {
+        const bool cin[2] = {ADJ ? (X < g.Wu) : (X >= C::P && X < C::P + g.N),
+                             ADJ ? (X + 1 < g.Wu) : (X + 1 >= C::P && X + 1 < C::P + g.N)};
+#pragma unroll
+        for (int q = 0; q < NTASK; ++q) {
+          const float4 zz = *reinterpret_cast<const float4*>(OB + (er + 8 * q) * FFT_PITCH + C::P4 + 2 * ep);   // 2 complex
+          const float v[2][2] = {{zz.x, zz.z}, {zz.y, zz.w}};                                                   // [h][column]
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int Y = Ybase + 8 * q + h * C::HB;
+            if (Y >= yend) continue;
+            const float av[2] = {pa[q][h].x, pa[q][h].y};
+            float o[2];
+            if (!ADJ) {
+              const int gy = g.row0 + Y;
+              const bool rowin = (gy >= C::P) && (gy < C::P + g.M);
+#pragma unroll
+              for (int j = 0; j < 2; ++j) o[j] = (rowin && cin[j]) ? v[h][j] - av[j] : 0.f;
+            } else {
+              const float bv[2] = {pb[q][h].x, pb[q][h].y};
+              const bool owned = Y >= g.own0 && Y < g.own1;
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                o[j] = cin[j] ? v[h][j] : 0.f;
+                if (cin[j] && owned) {
+                  const float G = fmaf(lambd, v[h][j], 0.5f * (av[j] - bv[j]));   // pyx:519
+                  mu = fmaxf(mu, av[j]);
+                  mG = fmaxf(mG, fabsf(G));
+                }
+              }
+            }
+            *reinterpret_cast<float2*>(op + size_t(8 * q + h * C::HB) * g.pitch) = make_float2(o[0], o[1]);
+          }
         }
       }
     }
     __syncthreads();   // stage s (now holding O) and ZB are free again
+    mark(4);
     if (ADJ) {
       const int tn = t + gridDim.x;
       const int cn = tn < ntiles ? tn / tiles_per_c : -1;
@@ -250,6 +290,8 @@ k_conv_fft(const __grid_constant__ CUtensorMap tm_in, const float* __restrict__ 
       }
     }
   }
+  if (tid == 0)
+    for (int i = 0; i < 6; ++i) atomicAdd(&g_fft_phase_cycles[i], (unsigned long long)ph[i]);
   if (ADJ && cp.nranks > 1) {
     __threadfence();
     __syncthreads();

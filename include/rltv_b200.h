@@ -164,6 +164,8 @@ int rltv_stage_gradk(rltv_ctx* ctx, float* gk_out /* packed (MK,MK,3) */);
 /* TV(u, out, M, N, epsilon, order, norm, div) (pyx:137-239) of the estimate on the device; order, norm in {1,2};
  * out/div: packed HWC (M+MK-1, N+MK-1, 3), zero on the border ring; *ms = device time of the stencil kernel */
 int rltv_stage_tv(rltv_ctx* ctx, int32_t order, int32_t norm, float epsilon, float* out, float* div, float* ms);
+/* debug: cycles spent per phase of the row-FFT stencil kernel since the last call (8 counters), then reset */
+int rltv_debug_phase_cycles(uint64_t* out8);
 /* test entry point of the shared-memory FFT engine used by the row-FFT stencils: nrows x 128 complex values
  * (interleaved re, im), forward (exp(-i..)) or unnormalised inverse */
 int rltv_debug_fft128(const float* in, float* out, int32_t nrows, int32_t inverse, int32_t device);
