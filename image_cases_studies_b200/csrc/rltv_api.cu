@@ -221,7 +221,7 @@ int launch_conv_fft_t(rltv_ctx* c, float lambd) {
     CU(cudaFuncSetAttribute(k_conv_fft<K, ADJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     const int y0 = ADJ ? c->g.own0 : c->fwd0, y1 = ADJ ? c->g.own1 : c->fwd1;
     const int ntx = (c->g.Wu + C::TWO - 1) / C::TWO, nty = (y1 - y0 + C::TROWS - 1) / C::TROWS;
-    int grid = c->num_sms;
+    int grid = 2 * c->num_sms;
     if (grid > 3 * ntx * nty) grid = 3 * ntx * nty;
     ProfScope p(c, ADJ ? F_CONV_ADJ : F_CONV_FWD);
     if (ADJ) {

@@ -6,14 +6,15 @@
 // the y direction stays a direct sum -- but of SPECTRA:   Out^[Y] = sum_ky Wc[ky] (.) In^[Y-P+ky]   -> K complex MACs
 // per (row, bin) = 4K FMAs per 112/128 outputs instead of K*K: 34 instead of 225 FMAs per output at K = 15, plus two
 // 128-point FFTs per row.  Because the taps are real, two image rows ride through the complex FFT as real and
-// imaginary parts (rows Y and Y+48 of a 96-row tile) and come out as the real and imaginary parts of the inverse
+// imaginary parts (rows Y and Y+24 of a 48-row tile) and come out as the real and imaginary parts of the inverse
 // transform: no real-FFT untangling anywhere.
 //
-// Per 96 x 112 output tile (one CTA of 512 threads per SM, persistent, TMA double-buffered input like k_conv):
-//   1. forward FFT of the 48+K-1 packed rows straight out of the TMA buffer          (csrc/rltv_fft.cuh)
-//   2. vertical MAC over spectra: thread = (bin, chunk of 12 output rows), K complex taps in registers
-//   3. inverse FFT of the 48 packed output rows (into the consumed TMA buffer)
-//   4. epilogue as in k_conv (residual / step statistics), 112 columns x 96 rows, operands read from global memory
+// Per 48 x 112 output tile (CTAs of 384 threads, two per SM so that the FFT phases of one overlap the MAC of the
+// other; persistent; one TMA stage that is re-armed as soon as the forward FFTs have consumed it):
+//   1. forward FFT of the 24+K-1 packed rows straight out of the TMA buffer          (csrc/rltv_fft.cuh)
+//   2. vertical MAC over spectra, in place: thread = (bin, chunk of 8 output rows), tap spectra in shared memory
+//   3. inverse FFT of the 24 packed output rows
+//   4. epilogue as in k_conv (residual / step statistics), 112 columns x 48 rows, operands prefetched to registers
 #pragma once
 #include "rltv_band.cuh"
 #include "rltv_common.cuh"
@@ -29,21 +30,22 @@ struct FftCfg {
   static constexpr int P = K / 2;
   static constexpr int P4 = (P + 3) & ~3;          // 16-byte aligned TMA box start
   static constexpr int TWO = 112;                  // valid output columns per 128-sample segment
-  static constexpr int HB = 48;                    // rows per packed block (real part: rows 0..47, imaginary: 48..95)
+  static constexpr int HB = 24;                    // rows per packed block (real part: rows 0..23, imaginary: 24..47)
   static constexpr int TROWS = 2 * HB;
   static constexpr int IN_ROWS = TROWS + K - 1;    // TMA box height (real rows)
   static constexpr int ZROWS = HB + K - 1;         // packed complex rows
-  static constexpr int CHUNK = 12;                 // output rows per MAC thread (4 chunks x 128 bins = 512 threads)
-  static constexpr int THREADS = 512;
+  static constexpr int THREADS = 384;              // 12 warps; two CTAs per SM run their phases out of step
+  static constexpr int NCHUNK = THREADS / FFT_N;   // MAC: 128 bins x 3 row chunks
+  static constexpr int CHUNK = HB / NCHUNK;        // output rows per MAC thread
+  static constexpr int ER = THREADS / (TWO / 2);   // epilogue: 6 row slots x 56 column pairs
+  static constexpr int NTASK = HB / ER;
   static constexpr int IN_BYTES = IN_ROWS * FFT_N * 4;                        // TMA transaction size
   static constexpr int ZB_BYTES = ZROWS * FFT_PITCH * 8;
-  static constexpr int OB_BYTES = HB * FFT_PITCH * 8;
-  static constexpr int STAGE_BYTES = IN_BYTES > OB_BYTES ? IN_BYTES : OB_BYTES;   // the output spectra reuse the stage
-  static_assert(P4 + TWO - 1 + P <= FFT_N - 1, "segment too short for this K");
-  static_assert(OB_BYTES <= STAGE_BYTES, "output spectra alias the consumed input stage");
-  static_assert(STAGE_BYTES % 128 == 0 && ZB_BYTES % 128 == 0, "TMA destinations: 128-byte aligned");
-  static_assert(4 * CHUNK == HB && HB % 8 == 0, "MAC chunks / epilogue row slots cover the packed rows");
-  static constexpr int SMEM_BYTES = 2 * STAGE_BYTES + ZB_BYTES + FFT_N * 8 + 64 + 128;
+  static constexpr int WS_BYTES = K * FFT_N * 8;                              // tap spectra of the current channel
+  static_assert(NCHUNK * CHUNK == HB && ER * NTASK == HB, "MAC chunks / epilogue row slots cover the packed rows");
+  static_assert(IN_BYTES % 128 == 0 && ZB_BYTES % 128 == 0 && WS_BYTES % 128 == 0, "TMA destinations: 128-byte aligned");
+  static constexpr int SMEM_BYTES = IN_BYTES + ZB_BYTES + WS_BYTES + FFT_N * 8 + 64 + 128;
+  static_assert(2 * SMEM_BYTES <= 227 * 1024, "two CTAs per SM");
 };
 
 // Tap spectra: wspec[dir][c][ky][k] = (1/128) sum_{j=-P..P} w[ky][j+P] exp(+2 pi i j k / 128), w = rot180(psf) for
@@ -69,7 +71,7 @@ k_psf_spectrum(const State* __restrict__ st, const float* __restrict__ psf, int 
 __device__ unsigned long long g_fft_phase_cycles[8];
 
 template <int K, bool ADJ>
-__global__ void __launch_bounds__(FftCfg<K>::THREADS, 1)
+__global__ void __launch_bounds__(FftCfg<K>::THREADS, 2)
 k_conv_fft(const __grid_constant__ CUtensorMap tm_in, const float* __restrict__ e0g, const float* __restrict__ e1g,
            Geom g, State* __restrict__ st, const float2* __restrict__ wspec,
            float lambd, float* __restrict__ out, int ntx, int nty, int ybeg, int yend, CommPeers cp, int seq,
@@ -78,9 +80,11 @@ k_conv_fft(const __grid_constant__ CUtensorMap tm_in, const float* __restrict__ 
   if (st->stop) return;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
-  float2* ZB = reinterpret_cast<float2*>(smem + 2 * C::STAGE_BYTES);
-  float2* tw = reinterpret_cast<float2*>(smem + 2 * C::STAGE_BYTES + C::ZB_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(tw) + FFT_N * 8);
+  const float* inR = reinterpret_cast<const float*>(smem);                       // real rows, TMA destination
+  float2* ZB = reinterpret_cast<float2*>(smem + C::IN_BYTES);                    // packed spectra, then outputs
+  float2* WS = reinterpret_cast<float2*>(smem + C::IN_BYTES + C::ZB_BYTES);      // tap spectra [K][128]
+  float2* tw = reinterpret_cast<float2*>(smem + C::IN_BYTES + C::ZB_BYTES + C::WS_BYTES);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(tw) + FFT_N * 8);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tiles_per_c = ntx * nty, ntiles = 3 * tiles_per_c;
 
@@ -89,110 +93,106 @@ k_conv_fft(const __grid_constant__ CUtensorMap tm_in, const float* __restrict__ 
     st->max_G[tid] = 0;
   }
   if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
+    mbar_init(bar, 1);
     fence_mbar_init();
     tma_prefetch_desc(&tm_in);
   }
   fft_fill_twiddles(tw);
   __syncthreads();
 
-  auto issue_in = [&](int t, int s) {
+  auto issue_in = [&](int t) {
     const int c = t / tiles_per_c, r = t - c * tiles_per_c;
     const int by = r / ntx, bx = r - by * ntx;
-    mbar_arrive_expect_tx(&bars[s], C::IN_BYTES);
-    tma_load_3d(smem + s * C::STAGE_BYTES, &tm_in, bx * C::TWO - C::P4, ybeg + by * C::TROWS - C::P, c, &bars[s]);
+    mbar_arrive_expect_tx(bar, C::IN_BYTES);
+    tma_load_3d(smem, &tm_in, bx * C::TWO - C::P4, ybeg + by * C::TROWS - C::P, c, bar);
   };
-  // MAC role of this thread: frequency bin and chunk of output rows
-  const int bin = tid & (FFT_N - 1), chunk = tid >> 7;          // 4 chunks x 12 rows = 48 packed output rows
-  float2 wreg[K];
-  // epilogue role: 8 row slots x 56 column pairs = 448 of the 512 threads
+  // MAC role of this thread: frequency bin and chunk of output rows; epilogue role: row slot and column pair
+  const int bin = tid & (FFT_N - 1), chunk = tid >> 7;
   const int er = tid / (C::TWO / 2), ep = tid - er * (C::TWO / 2);
-  const bool epi_active = er < 8;
+  const bool epi_active = er < C::ER;
 
   int t = blockIdx.x;
-  if (tid == 0 && t < ntiles) issue_in(t, 0);
+  if (tid == 0 && t < ntiles) issue_in(t);
   int cur_c = -1;
   float mu = -INFINITY, mG = 0.f;
   long long ph[6] = {0, 0, 0, 0, 0, 0}, tprev = clock64();
   auto mark = [&](int i) { if (tid == 0) { const long long now = clock64(); ph[i] += now - tprev; tprev = now; } };
   for (int k = 0; t < ntiles; ++k, t += gridDim.x) {
-    const int s = k & 1;
     const int c = t / tiles_per_c, r = t - c * tiles_per_c;
     const int by = r / ntx, bx = r - by * ntx;
-    if (tid == 0) {
-      const int tn = t + gridDim.x;
-      if (tn < ntiles) issue_in(tn, s ^ 1);
-    }
     if (c != cur_c) {
-      const float2* wsrc = wspec + ((size_t(ADJ ? 1 : 0) * 3 + c) * K) * FFT_N + bin;
-#pragma unroll
-      for (int ky = 0; ky < K; ++ky) wreg[ky] = __ldg(wsrc + ky * FFT_N);
+      // tap spectra of this channel into shared memory (the previous tile's last barrier released WS)
+      const float2* wsrc = wspec + (size_t(ADJ ? 1 : 0) * 3 + c) * K * FFT_N;
+      for (int i = tid; i < K * FFT_N; i += C::THREADS) WS[i] = __ldg(wsrc + i);
       cur_c = c;
     }
-    mbar_wait(&bars[s], (k >> 1) & 1);
+    mbar_wait(bar, k & 1);
     mark(0);
 
     __syncwarp();
     // 1. forward FFT of the packed rows: Z[r] = in[r] + i in[r + HB], read straight from the TMA buffer
-    {
-      const float* inR = reinterpret_cast<const float*>(smem + s * C::STAGE_BYTES);
-      for (int task = tid; task < C::ZROWS * 8; task += C::THREADS) {
-        const unsigned mask = __activemask();
-        const int zr = task >> 3, tt = task & 7;
-        const float* ra = inR + zr * FFT_N;
-        const float* rb = inR + (zr + C::HB) * FFT_N;
-        fft128_row<false>(ZB + zr * FFT_PITCH, tw, tt, [&](int n) { return make_float2(ra[n], rb[n]); }, mask, zr & 3);
-      }
+    for (int task = tid; task < C::ZROWS * 8; task += C::THREADS) {
+      const unsigned mask = __activemask();
+      const int zr = task >> 3, tt = task & 7;
+      const float* ra = inR + zr * FFT_N;
+      const float* rb = inR + (zr + C::HB) * FFT_N;
+      fft128_row<false>(ZB + zr * FFT_PITCH, tw, tt, [&](int n) { return make_float2(ra[n], rb[n]); }, mask, zr & 3);
     }
     __syncthreads();
     mark(1);
+    if (tid == 0) {                         // the real-row stage is consumed: its reload overlaps everything below
+      const int tn = t + gridDim.x;
+      if (tn < ntiles) issue_in(tn);
+    }
 
-    // 2. vertical MAC over spectra: O[y][bin] = sum_ky Wc[ky][bin] * Z[y + ky][bin]; O overwrites the consumed stage
-    float2* OB = reinterpret_cast<float2*>(smem + s * C::STAGE_BYTES);
+    // 2. vertical MAC over spectra, in place: O[y][bin] = sum_ky Wc[ky][bin] * Z[y + ky][bin] -> ZB row y
     {
       float2 z[C::CHUNK + K - 1];
 #pragma unroll
       for (int i = 0; i < C::CHUNK + K - 1; ++i) z[i] = ZB[(chunk * C::CHUNK + i) * FFT_PITCH + bin];
+      float2 acc[C::CHUNK];
 #pragma unroll
-      for (int y = 0; y < C::CHUNK; ++y) {
-        float2 acc = make_float2(0.f, 0.f);
+      for (int y = 0; y < C::CHUNK; ++y) acc[y] = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int ky = 0; ky < K; ++ky) {
-          acc.x = fmaf(wreg[ky].x, z[y + ky].x, acc.x);
-          acc.x = fmaf(-wreg[ky].y, z[y + ky].y, acc.x);
-          acc.y = fmaf(wreg[ky].x, z[y + ky].y, acc.y);
-          acc.y = fmaf(wreg[ky].y, z[y + ky].x, acc.y);
+      for (int ky = 0; ky < K; ++ky) {
+        const float2 w = WS[ky * FFT_N + bin];
+#pragma unroll
+        for (int y = 0; y < C::CHUNK; ++y) {
+          acc[y].x = fmaf(w.x, z[y + ky].x, acc[y].x);
+          acc[y].x = fmaf(-w.y, z[y + ky].y, acc[y].x);
+          acc[y].y = fmaf(w.x, z[y + ky].y, acc[y].y);
+          acc[y].y = fmaf(w.y, z[y + ky].x, acc[y].y);
         }
-        OB[(chunk * C::CHUNK + y) * FFT_PITCH + bin] = acc;
       }
+      __syncthreads();                      // every chunk has read its window (chunks overlap by K-1 rows)
+#pragma unroll
+      for (int y = 0; y < C::CHUNK; ++y) ZB[(chunk * C::CHUNK + y) * FFT_PITCH + bin] = acc[y];
     }
     __syncthreads();
 
     // Epilogue operands of this thread's outputs go to registers now, so their DRAM latency hides behind the
-    // inverse FFT.  Epilogue thread = (row slot er of 8, column pair ep of 56): outputs (er + 8q [+ HB], 2ep..2ep+1).
-    constexpr int NTASK = C::HB / 8;
+    // inverse FFT.  Epilogue thread = (row slot er, column pair ep): outputs (er + ER*q [+ HB], 2ep..2ep+1).
     const int X = bx * C::TWO + 2 * ep;
     const int Ybase = ybeg + by * C::TROWS + er;
     const bool xok = epi_active && X < g.pitch;
     const size_t off0 = size_t(c) * g.plane + size_t(Ybase) * g.pitch + X;
-    float2 pa[NTASK][2], pb[ADJ ? NTASK : 1][2];
+    float2 pa[C::NTASK][2], pb[ADJ ? C::NTASK : 1][2];
 #pragma unroll
-    for (int q = 0; q < NTASK; ++q)
+    for (int q = 0; q < C::NTASK; ++q)
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        const bool ok = xok && (Ybase + 8 * q + h * C::HB) < yend;
-        const size_t goff = ok ? off0 + size_t(8 * q + h * C::HB) * g.pitch : 0;
+        const bool ok = xok && (Ybase + C::ER * q + h * C::HB) < yend;
+        const size_t goff = ok ? off0 + size_t(C::ER * q + h * C::HB) * g.pitch : 0;
         pa[q][h] = ok ? __ldg(reinterpret_cast<const float2*>(e0g + goff)) : make_float2(0.f, 0.f);
         if (ADJ) pb[q][h] = ok ? __ldg(reinterpret_cast<const float2*>(e1g + goff)) : make_float2(0.f, 0.f);
       }
-
     mark(2);
+
     // 3. inverse FFT of the packed output rows, in place
     for (int task = tid; task < C::HB * 8; task += C::THREADS) {
       const unsigned mask = __activemask();
       const int zr = task >> 3, tt = task & 7;
-      float2* row = OB + zr * FFT_PITCH;
+      float2* row = ZB + zr * FFT_PITCH;
       fft128_row<true>(row, tw, tt, [&](int n) { return row[n]; }, mask);
     }
     __syncthreads();
@@ -209,8 +209,8 @@ k_conv_fft(const __grid_constant__ CUtensorMap tm_in, const float* __restrict__ 
       if (interior) {
         if (epi_active) {
 #pragma unroll
-          for (int q = 0; q < NTASK; ++q) {
-            const float4 zz = *reinterpret_cast<const float4*>(OB + (er + 8 * q) * FFT_PITCH + C::P4 + 2 * ep);
+          for (int q = 0; q < C::NTASK; ++q) {
+            const float4 zz = *reinterpret_cast<const float4*>(ZB + (er + C::ER * q) * FFT_PITCH + C::P4 + 2 * ep);
             const float v[2][2] = {{zz.x, zz.z}, {zz.y, zz.w}};
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -224,7 +224,7 @@ k_conv_fft(const __grid_constant__ CUtensorMap tm_in, const float* __restrict__ 
                 mu = fmaxf(mu, fmaxf(pa[q][h].x, pa[q][h].y));
                 mG = fmaxf(mG, fmaxf(fabsf(G0), fabsf(G1)));
               }
-              *reinterpret_cast<float2*>(op + size_t(8 * q + h * C::HB) * g.pitch) = o;
+              *reinterpret_cast<float2*>(op + size_t(C::ER * q + h * C::HB) * g.pitch) = o;
             }
           }
         }
@@ -232,12 +232,12 @@ k_conv_fft(const __grid_constant__ CUtensorMap tm_in, const float* __restrict__ 
         const bool cin[2] = {ADJ ? (X < g.Wu) : (X >= C::P && X < C::P + g.N),
                              ADJ ? (X + 1 < g.Wu) : (X + 1 >= C::P && X + 1 < C::P + g.N)};
 #pragma unroll
-        for (int q = 0; q < NTASK; ++q) {
-          const float4 zz = *reinterpret_cast<const float4*>(OB + (er + 8 * q) * FFT_PITCH + C::P4 + 2 * ep);   // 2 complex
-          const float v[2][2] = {{zz.x, zz.z}, {zz.y, zz.w}};                                                   // [h][column]
+        for (int q = 0; q < C::NTASK; ++q) {
+          const float4 zz = *reinterpret_cast<const float4*>(ZB + (er + C::ER * q) * FFT_PITCH + C::P4 + 2 * ep);   // 2 complex
+          const float v[2][2] = {{zz.x, zz.z}, {zz.y, zz.w}};                                                       // [h][column]
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            const int Y = Ybase + 8 * q + h * C::HB;
+            const int Y = Ybase + C::ER * q + h * C::HB;
             if (Y >= yend) continue;
             const float av[2] = {pa[q][h].x, pa[q][h].y};
             float o[2];
@@ -259,12 +259,12 @@ k_conv_fft(const __grid_constant__ CUtensorMap tm_in, const float* __restrict__ 
                 }
               }
             }
-            *reinterpret_cast<float2*>(op + size_t(8 * q + h * C::HB) * g.pitch) = make_float2(o[0], o[1]);
+            *reinterpret_cast<float2*>(op + size_t(C::ER * q + h * C::HB) * g.pitch) = make_float2(o[0], o[1]);
           }
         }
       }
     }
-    __syncthreads();   // stage s (now holding O) and ZB are free again
+    __syncthreads();   // ZB and WS are free again
     mark(4);
     if (ADJ) {
       const int tn = t + gridDim.x;
@@ -275,8 +275,8 @@ k_conv_fft(const __grid_constant__ CUtensorMap tm_in, const float* __restrict__ 
         if (lane == 0) { red_u[warp] = wu; red_G[warp] = wG; }
         __syncthreads();
         if (warp == 0) {
-          float a = lane < 16 ? red_u[lane] : -INFINITY;
-          float b = lane < 16 ? red_G[lane] : 0.f;
+          float a = lane < C::THREADS / 32 ? red_u[lane] : -INFINITY;
+          float b = lane < C::THREADS / 32 ? red_G[lane] : 0.f;
           a = warp_max(a);
           b = warp_max(b);
           if (lane == 0) {
