@@ -80,7 +80,8 @@ struct rltv_ctx {
   double2* gkf_gpart = nullptr; // per-group sums + final scratch
   unsigned* gkf_tickets = nullptr;
   float2* wspec = nullptr;      // tap spectra [2][3][K][128]
-  bool use_fft = false;
+  bool use_fft = false;         // forward blur / adjoint through k_conv_fft
+  bool use_fft_gradk = false;   // PSF gradient through k_gradk_fft
   double* gk_sum = nullptr;
   // row bands: halo exchange + all-gathers through peer memory (rltv_band.cuh)
   HaloSide side[2]{};           // 0: band above, 1: band below
@@ -202,10 +203,12 @@ int make_maps_t(rltv_ctx* c) {
   if ((rc = make_tmap(&c->tm_u_gk, c->u, g, g.Hu, G::SP, G::SROWS))) return rc;
   // residual as seen by the PSF gradient: OWNED rows only (halo rows read as zero)
   if ((rc = make_tmap(&c->tm_err_gk, c->err + size_t(g.own0) * g.pitch, g, g.own1 - g.own0, G::TW, G::TH))) return rc;
-  if constexpr (K >= 9 && K <= 17) {
+  if constexpr (K >= 9) {
     using F = FftCfg<K>;
     if ((rc = make_tmap(&c->tm_u_fft, c->u, g, g.Hu, FFT_N, F::IN_ROWS))) return rc;
     if ((rc = make_tmap(&c->tm_err_fft, c->err, g, g.Hu, FFT_N, F::IN_ROWS))) return rc;
+  }
+  if constexpr (K >= 9) {
     using GF = GradkFftCfg<K>;
     if ((rc = make_tmap(&c->tm_u_gkfft, c->u, g, g.Hu, FFT_N, GF::U_ROWS))) return rc;
     if ((rc = make_tmap(&c->tm_err_gkfft, c->err + size_t(g.own0) * g.pitch, g, g.own1 - g.own0, FFT_N, GF::TROWS))) return rc;
@@ -215,13 +218,13 @@ int make_maps_t(rltv_ctx* c) {
 
 template <int K, bool ADJ>
 int launch_conv_fft_t(rltv_ctx* c, float lambd) {
-  if constexpr (K >= 9 && K <= 17) {
+  if constexpr (K >= 9) {
     using C = FftCfg<K>;
     constexpr int SMEM = C::SMEM_BYTES;
     CU(cudaFuncSetAttribute(k_conv_fft<K, ADJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     const int y0 = ADJ ? c->g.own0 : c->fwd0, y1 = ADJ ? c->g.own1 : c->fwd1;
     const int ntx = (c->g.Wu + C::TWO - 1) / C::TWO, nty = (y1 - y0 + C::TROWS - 1) / C::TROWS;
-    int grid = 2 * c->num_sms;
+    int grid = C::CTAS_PER_SM * c->num_sms;
     if (grid > 3 * ntx * nty) grid = 3 * ntx * nty;
     ProfScope p(c, ADJ ? F_CONV_ADJ : F_CONV_FWD);
     if (ADJ) {
@@ -234,7 +237,7 @@ int launch_conv_fft_t(rltv_ctx* c, float lambd) {
     }
     return RLTV_OK;
   } else {
-    return fail(RLTV_ERR_ARG, "row-FFT stencils exist for 9 <= MK <= 17");
+    return fail(RLTV_ERR_ARG, "row-FFT stencils exist for MK >= 9");
   }
 }
 
@@ -270,7 +273,7 @@ int launch_conv_t(rltv_ctx* c, float lambd) {
 
 template <int K>
 int launch_gradk_fft_t(rltv_ctx* c) {
-  if constexpr (K >= 9 && K <= 17) {
+  if constexpr (K >= 9) {
     using C = GradkFftCfg<K>;
     CU(cudaFuncSetAttribute(k_gradk_fft<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     const int ntx = (c->g.Wu + C::TWO - 1) / C::TWO, nty = (c->g.own1 - c->g.own0 + C::TROWS - 1) / C::TROWS;
@@ -281,13 +284,13 @@ int launch_gradk_fft_t(rltv_ctx* c) {
                                                                          c->peers, c->gk_seq);
     return RLTV_OK;
   } else {
-    return fail(RLTV_ERR_ARG, "row-FFT stencils exist for 9 <= MK <= 17");
+    return fail(RLTV_ERR_ARG, "row-FFT stencils exist for MK >= 9");
   }
 }
 
 template <int K>
 int launch_gradk_t(rltv_ctx* c) {
-  if (c->use_fft) return launch_gradk_fft_t<K>(c);
+  if (c->use_fft_gradk) return launch_gradk_fft_t<K>(c);
   using C = GradkCfg<K>;
   CU(cudaFuncSetAttribute(k_gradk<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   const int ntx = (c->g.Wu + C::TW - 1) / C::TW, nty = (c->g.own1 - c->g.own0 + C::TH - 1) / C::TH;
@@ -652,9 +655,10 @@ int rltv_create_band(rltv_ctx** out, int32_t device, int32_t M, int32_t N, int32
   {
     // Row-FFT hybrid stencils (csrc/rltv_stencil_fft.cuh) for the FP32-bound sizes; RLTV_CONV=direct|fft overrides
     const char* e = getenv("RLTV_CONV");
-    c->use_fft = (MK >= 11 && MK <= 17);
+    c->use_fft = (MK >= 11);
     if (e && !strcmp(e, "direct")) c->use_fft = false;
-    if (e && !strcmp(e, "fft") && MK >= 9 && MK <= 17) c->use_fft = true;
+    if (e && !strcmp(e, "fft") && MK >= 9) c->use_fft = true;
+    c->use_fft_gradk = c->use_fft;
   }
   {
     int rc = make_maps(c);

@@ -1,4 +1,4 @@
-// Row-FFT hybrid stencils for 9 <= K <= 17: the FLOP-reducing form of the forward blur and the adjoint
+// Row-FFT hybrid stencils for 9 <= K <= 31 (forward blur, adjoint) and 9 <= K <= 17 (PSF gradient): the FLOP-reducing form of the forward blur and the adjoint
 // (lib/deconvolution.pyx:477-491, :557-565), which the reference itself evaluates as FFT convolutions (scipy).
 //
 // A K x K stencil  out[Y][X] = sum_{ky,kx} w[ky][kx] in[Y-P+ky][X-P+kx]  costs K*K FMAs per output directly.  Here the
@@ -26,10 +26,11 @@ namespace rltv {
 
 template <int K>
 struct FftCfg {
-  static_assert(K >= 9 && K <= 17, "128-sample segments hold 112 outputs + K-1 halo only up to K = 17");
+  static_assert(K >= 9 && K <= 31, "128-sample segments: 112 outputs + halo up to K = 17, 96 outputs up to K = 31");
   static constexpr int P = K / 2;
   static constexpr int P4 = (P + 3) & ~3;          // 16-byte aligned TMA box start
-  static constexpr int TWO = 112;                  // valid output columns per 128-sample segment
+  static constexpr int TWO = (K <= 17) ? 112 : 96; // valid output columns per 128-sample segment
+  static constexpr int CTAS_PER_SM = (K <= 17) ? 2 : 1;
   static constexpr int HB = 24;                    // rows per packed block (real part: rows 0..23, imaginary: 24..47)
   static constexpr int TROWS = 2 * HB;
   static constexpr int IN_ROWS = TROWS + K - 1;    // TMA box height (real rows)
@@ -45,7 +46,8 @@ struct FftCfg {
   static_assert(NCHUNK * CHUNK == HB && ER * NTASK == HB, "MAC chunks / epilogue row slots cover the packed rows");
   static_assert(IN_BYTES % 128 == 0 && ZB_BYTES % 128 == 0 && WS_BYTES % 128 == 0, "TMA destinations: 128-byte aligned");
   static constexpr int SMEM_BYTES = IN_BYTES + ZB_BYTES + WS_BYTES + FFT_N * 8 + 64 + 128;
-  static_assert(2 * SMEM_BYTES <= 227 * 1024, "two CTAs per SM");
+  static_assert(P4 + TWO - 1 + P <= FFT_N - 1, "segment too short for this K");
+  static_assert(CTAS_PER_SM * SMEM_BYTES <= 227 * 1024, "shared memory");
 };
 
 // Tap spectra: wspec[dir][c][ky][k] = (1/128) sum_{j=-P..P} w[ky][j+P] exp(+2 pi i j k / 128), w = rot180(psf) for
@@ -71,7 +73,7 @@ k_psf_spectrum(const State* __restrict__ st, const float* __restrict__ psf, int 
 __device__ unsigned long long g_fft_phase_cycles[8];
 
 template <int K, bool ADJ>
-__global__ void __launch_bounds__(FftCfg<K>::THREADS, 2)
+__global__ void __launch_bounds__(FftCfg<K>::THREADS, FftCfg<K>::CTAS_PER_SM)
 k_conv_fft(const __grid_constant__ CUtensorMap tm_in, const float* __restrict__ e0g, const float* __restrict__ e1g,
            Geom g, State* __restrict__ st, const float2* __restrict__ wspec,
            float lambd, float* __restrict__ out, int ntx, int nty, int ybeg, int yend, CommPeers cp, int seq,
@@ -318,27 +320,31 @@ namespace rltv {
 //   Rows are packed in pairs like in k_conv_fft (Z = row y + i row y+HB); the packed product equals A + iB with
 //   A = conj(E)U + conj(E')U' (wanted) and B a cross term; both are spectra of real sequences, hence
 //   A[k] = (C[k] + conj(C[-k])) / 2 -- untangled once, by the last CTA, before a 15-lag inverse DFT in double.
-// Per 80 x 112 tile: 94 forward row FFTs + 40*128*K complex MACs; no inverse FFT, no epilogue.
+// Per 80 x 112 tile (K <= 17; 64 x 96 above): forward row FFTs + HB*128*K complex MACs; no inverse FFT, no epilogue.
 // One real-data stage only: the next tile's TMA is issued as soon as the forward FFTs have consumed the stage and
 // overlaps the MAC phase.
 // ------------------------------------------------------------------------------------------------
 template <int K>
 struct GradkFftCfg {
-  static_assert(K >= 9 && K <= 17, "see FftCfg");
+  static_assert(K >= 9 && K <= 31, "see FftCfg");
   static constexpr int P = K / 2;
   static constexpr int P4 = (P + 3) & ~3;
-  static constexpr int TWO = 112;
-  static constexpr int HB = 40;
+  static constexpr int TWO = (K <= 17) ? 112 : 96;
+  static constexpr int HB = (K <= 17) ? 40 : 32;
+  static constexpr int THREADS = (K <= 17) ? 512 : 256;   // large K: 2K complex accumulators + a K-deep window per thread
   static constexpr int TROWS = 2 * HB;
   static constexpr int U_ROWS = TROWS + K - 1;      // real u rows per tile
   static constexpr int ZU_ROWS = HB + K - 1;
-  static constexpr int CHUNK = HB / 4;
-  static constexpr int THREADS = 512;
+  static constexpr int NCH = THREADS / FFT_N;
+  static constexpr int CHUNK = HB / NCH;
   static constexpr int U_BYTES = U_ROWS * FFT_N * 4;
   static constexpr int E_BYTES = TROWS * FFT_N * 4;
   static constexpr int ZU_BYTES = ZU_ROWS * FFT_PITCH * 8;
   static constexpr int ZE_BYTES = HB * FFT_PITCH * 8;
   static constexpr int SMEM_BYTES = U_BYTES + E_BYTES + ZU_BYTES + ZE_BYTES + FFT_N * 8 + 64 + 128;
+  static_assert(NCH * CHUNK == HB, "row chunks cover the packed rows");
+  static_assert(NCH * K * FFT_N * 8 <= ZU_BYTES + ZE_BYTES, "chunk-reduction scratch fits the spectra buffers");
+  static_assert(P4 + TWO - 1 + P <= FFT_N - 1, "segment too short for this K");
   static_assert(U_BYTES % 128 == 0 && E_BYTES % 128 == 0 && ZU_BYTES % 128 == 0 && ZE_BYTES % 128 == 0, "alignment");
   static_assert(SMEM_BYTES <= 227 * 1024, "does not fit shared memory");
   static constexpr int GROUP = 16;                  // CTAs per first-level reduction group
@@ -413,27 +419,31 @@ k_gradk_fft(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
     }
     __syncthreads();
     if (tid == 0 && q + 1 < total) issue(q + 1);      // the real-data stage is free: overlap the load with the MAC
-    // MAC: C[dy][bin] += conj(Ze[y][bin]) * Zu[y + dy][bin]
+    // MAC: C[dy][bin] += conj(Ze[y][bin]) * Zu[y + dy][bin]; a K-deep register window slides down the packed u rows
     {
-      float2 zu[C::CHUNK + K - 1];
+      const float2* zu0 = ZU + (chunk * C::CHUNK) * FFT_PITCH + bin;
+      const float2* ze0 = ZE + (chunk * C::CHUNK) * FFT_PITCH + bin;
+      float2 win[K];
 #pragma unroll
-      for (int i = 0; i < C::CHUNK + K - 1; ++i) zu[i] = ZU[(chunk * C::CHUNK + i) * FFT_PITCH + bin];
+      for (int i = 0; i < K - 1; ++i) win[i] = zu0[i * FFT_PITCH];
 #pragma unroll
       for (int y = 0; y < C::CHUNK; ++y) {
-        const float2 e = ZE[(chunk * C::CHUNK + y) * FFT_PITCH + bin];
+        win[(y + K - 1) % K] = zu0[(y + K - 1) * FFT_PITCH];
+        const float2 e = ze0[y * FFT_PITCH];
 #pragma unroll
         for (int d = 0; d < K; ++d) {
-          acc[d].x = fmaf(e.x, zu[y + d].x, acc[d].x);
-          acc[d].x = fmaf(e.y, zu[y + d].y, acc[d].x);
-          acc[d].y = fmaf(e.x, zu[y + d].y, acc[d].y);
-          acc[d].y = fmaf(-e.y, zu[y + d].x, acc[d].y);
+          const float2 z = win[(y + d) % K];
+          acc[d].x = fmaf(e.x, z.x, acc[d].x);
+          acc[d].x = fmaf(e.y, z.y, acc[d].x);
+          acc[d].y = fmaf(e.x, z.y, acc[d].y);
+          acc[d].y = fmaf(-e.y, z.x, acc[d].y);
         }
       }
     }
     __syncthreads();      // ZU / ZE are free for the next tile
     const int c = q / my_tiles;
     if (q + 1 == total || (q + 1) / my_tiles != c) {
-      // end of a channel: fold the 4 row chunks (fixed order) through ZU and write this CTA's partial
+      // end of a channel: fold the row chunks (fixed order) through the spectra buffers and write this CTA's partial
       float2* red = ZU;   // [chunk][K][128]
 #pragma unroll
       for (int d = 0; d < K; ++d) {
@@ -444,7 +454,7 @@ k_gradk_fft(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
       for (int o = tid; o < K * FFT_N; o += C::THREADS) {
         float2 s0 = red[o];
 #pragma unroll
-        for (int ch = 1; ch < 4; ++ch) {
+        for (int ch = 1; ch < C::NCH; ++ch) {
           const float2 v = red[ch * K * FFT_N + o];
           s0.x += v.x;
           s0.y += v.y;

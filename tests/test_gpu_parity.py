@@ -251,7 +251,7 @@ def test_fft128_engine(inverse):
     assert np.abs(out - ref).max() <= 2e-5 * np.abs(ref).max()
 
 
-@pytest.mark.parametrize("K", [9, 11, 13, 15, 17])
+@pytest.mark.parametrize("K", [9, 11, 13, 15, 17, 19, 25, 31])
 def test_row_fft_stencils_against_oracle(K, monkeypatch):
     """k_conv_fft (row-FFT hybrid forward blur / adjoint, csrc/rltv_stencil_fft.cuh) against the float64 definition."""
     from image_cases_studies_b200.solver import Solver
