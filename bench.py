@@ -383,7 +383,7 @@ def main():
                 stats = dc.last_stats
             else:
                 rl_dist.richardson_lucy_MM(img_h, u_h, psf_h, *case.window, case.tau, M, N, 3, K, iters,
-                                           case.step_factor, case.lambd, blind=case.blind, comm=args.comm)
+                                           case.step_factor, case.lambd, blind=case.blind, comm=args.comm, gather="root")
                 stats = rl_dist.richardson_lucy_MM.last_stats
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
@@ -399,9 +399,11 @@ def main():
                "h2d_bytes_per_step": h2d if world == 1 else h2d // world, "d2h_bytes_per_step": d2h if world == 1 else d2h // world,
                "step": f"one richardson_lucy_MM call of {iters} outer iterations "
                f"({done_iters // max(args.e2e_calls, 1)} executed) on pinned host arrays"
-               + ("" if world == 1 else "; per-rank band up/download + NCCL gather of the result to every rank"),
+               + ("" if world == 1 else "; per-rank band upload/download, result bands gathered on rank 0 over NCCL"),
                "calls": args.e2e_calls, "seconds_per_call": secs / max(args.e2e_calls, 1), "gpu_launches_per_call": launches_call}
         dc.clear_cache()
+        if world > 1:
+            rl_dist.clear_cache()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

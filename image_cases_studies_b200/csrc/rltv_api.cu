@@ -648,7 +648,7 @@ int rltv_create_band(rltv_ctx** out, int32_t device, int32_t M, int32_t N, int32
   {
     const int ngroups = (c->gk_nparts + 15) / 16;
     CU(cudaMalloc(&c->gkf_part, size_t(c->gk_nparts) * 3 * MK * FFT_N * sizeof(float2)));
-    CU(cudaMalloc(&c->gkf_gpart, size_t(ngroups + 1) * 3 * MK * FFT_N * sizeof(double2)));
+    CU(cudaMalloc(&c->gkf_gpart, size_t(ngroups + 2) * 3 * MK * FFT_N * sizeof(double2)));   // groups + total + untangled
     CU(cudaMalloc(&c->gkf_tickets, size_t(ngroups + 1) * sizeof(unsigned)));
     CU(cudaMemsetAsync(c->gkf_tickets, 0, size_t(ngroups + 1) * sizeof(unsigned), c->stream));
   }

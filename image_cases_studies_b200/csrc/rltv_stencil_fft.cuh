@@ -510,20 +510,35 @@ k_gradk_fft(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
   __threadfence();
   __syncthreads();
   const int par = seq & 1;
+  // exp(+2 pi i m / 128) in double, once (the spectra buffers are free by now)
+  double2* tw64 = reinterpret_cast<double2*>(smem + C::U_BYTES + C::E_BYTES);
+  for (int m = tid; m < FFT_N; m += C::THREADS) {
+    double sn, cs;
+    sincospi(2.0 * double(m) / double(FFT_N), &sn, &cs);
+    tw64[m] = make_double2(cs, sn);
+  }
+  // untangle once per (c, dy, k): A[k] = (C[k] + conj(C[-k])) / 2, stored back over tot (second half of the scratch)
+  double2* Aun = tot + size_t(3) * K * FFT_N;
+  for (int o = tid; o < 3 * K * FFT_N; o += C::THREADS) {
+    const int k = o & (FFT_N - 1);
+    const double2 a = tot[o], b = tot[o - k + ((FFT_N - k) & (FFT_N - 1))];
+    Aun[o] = make_double2(0.5 * (a.x + b.x), 0.5 * (a.y - b.y));
+  }
+  __threadfence();
+  __syncthreads();
   for (int o = tid; o < 3 * K * K; o += C::THREADS) {
     const int c = o / (K * K), r = o - c * K * K;
     const int dy = r / K, dx = r - dy * K;
     const int s = dx - C::P;
-    const double2* row = tot + (size_t(c) * K + dy) * FFT_N;
-    double sum = 0.0;
-    for (int k = 0; k < FFT_N; ++k) {
-      const double2 a = row[k], b = row[(FFT_N - k) & (FFT_N - 1)];
-      const double ar = 0.5 * (a.x + b.x), ai = 0.5 * (a.y - b.y);      // A[k]
-      double sn, cs;
-      sincospi(2.0 * double((k * s) & (FFT_N - 1)) / double(FFT_N), &sn, &cs);
-      sum += ar * cs - ai * sn;                                           // Re(A[k] e^{+2 pi i k s / N})
+    const double2* row = Aun + (size_t(c) * K + dy) * FFT_N;
+    double s0 = 0.0, s1 = 0.0;
+    for (int k = 0; k < FFT_N; k += 2) {                                  // Re(A[k] e^{+2 pi i k s / N}), two chains
+      const double2 a0 = row[k], a1 = row[k + 1];
+      const double2 w0 = tw64[(k * s) & (FFT_N - 1)], w1 = tw64[((k + 1) * s) & (FFT_N - 1)];
+      s0 += a0.x * w0.x - a0.y * w0.y;
+      s1 += a1.x * w1.x - a1.y * w1.y;
     }
-    sum *= 1.0 / double(FFT_N);
+    const double sum = (s0 + s1) * (1.0 / double(FFT_N));
     gk_sum[o] = sum;
     if (cp.nranks > 1)
       for (int rr = 0; rr < cp.nranks; ++rr) cp.peer[rr]->gk_val[par][cp.rank][o] = sum;

@@ -147,8 +147,9 @@ class BandSolver:
                                            ub.strides[0], nat.ptr(psf)))
         self.dist.barrier(group=self.group)          # halos on every rank come from the same host frame
 
-    def download(self, u, psf_caller=None, psf_refined=None, gather=True):
-        """Writes this band's owned rows into ``u``; with ``gather`` every rank ends up with the full frame."""
+    def download(self, u, psf_caller=None, psf_refined=None, gather="all"):
+        """Writes this band's owned rows into ``u``.  gather="all": every rank ends up with the full frame (the SPMD
+        drop-in contract); "root": only rank 0 does (the other ranks keep their own band); False/None: no exchange."""
         torch, dist = self.torch, self.dist
         own_lo, own_hi = self.band[2], self.band[3]
         rows = u[own_lo:own_hi]
@@ -164,15 +165,29 @@ class BandSolver:
             psf_caller[...] = pc
         if psf_refined is not None and pr is not psf_refined:
             psf_refined[...] = pr
+        if gather is True:
+            gather = "all"
         if gather and self.world > 1:
             dev = f"cuda:{self.device}"
-            for r, b in enumerate(self.bands):
-                t = torch.empty((b[3] - b[2], u.shape[1], 3), dtype=torch.float32, device=dev)
-                if r == self.rank:
-                    t.copy_(torch.from_numpy(np.ascontiguousarray(u[b[2]:b[3]])))
-                dist.broadcast(t, src=dist.get_global_rank(self.group, r) if self.group is not None else r, group=self.group)
-                if r != self.rank:
-                    u[b[2]:b[3]] = t.cpu().numpy()
+            grank = (lambda r: dist.get_global_rank(self.group, r)) if self.group is not None else (lambda r: r)
+            if gather == "all":
+                for r, b in enumerate(self.bands):
+                    t = torch.empty((b[3] - b[2], u.shape[1], 3), dtype=torch.float32, device=dev)
+                    if r == self.rank:
+                        t.copy_(torch.from_numpy(np.ascontiguousarray(u[b[2]:b[3]])))
+                    dist.broadcast(t, src=grank(r), group=self.group)
+                    if r != self.rank:
+                        u[b[2]:b[3]] = t.cpu().numpy()
+            else:                                    # root: bands travel to rank 0 only (NCCL point to point)
+                if self.rank == 0:
+                    for r, b in enumerate(self.bands[1:], start=1):
+                        t = torch.empty((b[3] - b[2], u.shape[1], 3), dtype=torch.float32, device=dev)
+                        dist.recv(t, src=grank(r), group=self.group)
+                        u[b[2]:b[3]] = t.cpu().numpy()
+                else:
+                    b = self.band
+                    t = torch.from_numpy(np.ascontiguousarray(u[b[2]:b[3]])).to(dev)
+                    dist.send(t, dst=grank(0), group=self.group)
         return u
 
     # -- stepping ------------------------------------------------------------------------------------------
@@ -253,19 +268,35 @@ class BandSolver:
         return out
 
 
+_cache: dict = {}
+
+
+def clear_cache():
+    """Release the cached band contexts (collective: every rank must call it)."""
+    while _cache:
+        _cache.popitem()[1].close()
+
+
 def richardson_lucy_MM(image, u, psf, top, bottom, left, right, tau, M, N, C_, MK, iterations, step_factor, lambd,
-                       blind=True, correlation=False, group=None, comm="fused", **ignored):
+                       blind=True, correlation=False, group=None, comm="fused", gather="all", **ignored):
     """SPMD drop-in: every rank of the process group calls this with the same arrays; on return every rank's ``u``
-    and ``psf`` hold the full result, exactly as the single-GPU ``lib.deconvolution.richardson_lucy_MM`` leaves them."""
+    and ``psf`` hold the full result, exactly as the single-GPU ``lib.deconvolution.richardson_lucy_MM`` leaves them
+    (``gather="root"``: only rank 0's ``u`` is complete).  Band contexts (device buffers, IPC mappings) are cached per
+    geometry, like the single-GPU module caches its contexts; ``clear_cache()`` releases them."""
     M, N, MK = int(M), int(N), int(MK)
-    s = BandSolver(M, N, MK, (top, bottom, left, right), group=group, comm=comm)
+    key = (M, N, MK, int(top), int(bottom), int(left), int(right), comm, id(group))
+    s = _cache.get(key)
+    if s is None:
+        clear_cache()
+        s = _cache[key] = BandSolver(M, N, MK, (top, bottom, left, right), group=group, comm=comm)
     try:
         s.upload(image, u, psf)
         params = Solver.make_params((top, bottom, left, right), tau, iterations, step_factor, lambd, blind, correlation)
         stats = s.solve(params)
-        s.download(u, psf_caller=psf if blind else None, gather=True)
-    finally:
-        s.close()
+        s.download(u, psf_caller=psf if blind else None, gather=gather)
+    except Exception:
+        _cache.pop(key, None)
+        raise
     pad = (u.shape[0] - M) // 2
     richardson_lucy_MM.last_stats = stats
     return u[pad:pad + M, pad:pad + N, ...]

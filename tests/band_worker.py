@@ -59,6 +59,7 @@ def main():
             print("rank", rank, "mismatch", flag.item(), lo.tolist(), hi.tolist(), flush=True)
             dist.destroy_process_group()
             sys.exit(1)
+    distributed.clear_cache()
     if rank == 0 and len(sys.argv) > 1:
         Path(sys.argv[1]).write_text(json.dumps(report))
     dist.destroy_process_group()
