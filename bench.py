@@ -243,6 +243,7 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the frame (debugging only; invalid as a result)")
+    ap.add_argument("--frame", default=None, help="MxN override of the frame size (debugging only; invalid as a result)")
     ap.add_argument("--e2e-calls", type=int, default=2)
     ap.add_argument("--e2e-iterations", type=int, default=None)
     ap.add_argument("--comm", default="fused", choices=["fused", "nccl"],
@@ -273,7 +274,8 @@ def main():
     torch.cuda.set_device(dev)
     if args.frames > 0:
         return run_frame_batch(args, rank, dev, world)
-    case = synthetic.make_case(args.workload, seed=0, scale=args.scale)       # every rank builds the same frame
+    shape = tuple(int(v) for v in args.frame.lower().split("x")) if args.frame else None
+    case = synthetic.make_case(args.workload, seed=0, scale=args.scale, shape=shape)   # every rank builds the same frame
     M, N = case.shape
     K = case.MK
     params = Solver.make_params(case.window, case.tau, 10 ** 6, case.step_factor, case.lambd, case.blind)

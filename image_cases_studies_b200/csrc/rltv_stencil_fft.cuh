@@ -347,17 +347,13 @@ struct GradkFftCfg {
   static_assert(P4 + TWO - 1 + P <= FFT_N - 1, "segment too short for this K");
   static_assert(U_BYTES % 128 == 0 && E_BYTES % 128 == 0 && ZU_BYTES % 128 == 0 && ZE_BYTES % 128 == 0, "alignment");
   static_assert(SMEM_BYTES <= 227 * 1024, "does not fit shared memory");
-  static constexpr int GROUP = 16;                  // CTAs per first-level reduction group
 };
 
-// part   : [cta][c][dy][k] float2   per-CTA frequency-domain sums
-// gpart  : [group][c][dy][k] double2
-// tickets: [0 .. ngroups-1] per-group counters, [ngroups] final counter
+// part: [cta][c][dy][k] float2 per-CTA frequency-domain sums; k_gradk_fft_reduce / k_gradk_fft_final finish the job
 template <int K>
 __global__ void __launch_bounds__(GradkFftCfg<K>::THREADS, 1)
 k_gradk_fft(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_e, Geom g,
-            const State* __restrict__ st, float2* __restrict__ part, double2* __restrict__ gpart,
-            unsigned* __restrict__ tickets, int ntx, int nty, double* __restrict__ gk_sum, CommPeers cp, int seq) {
+            const State* __restrict__ st, float2* __restrict__ part, int ntx, int nty) {
   using C = GradkFftCfg<K>;
   if (st->stop) return;
   extern __shared__ unsigned char smem_raw[];
@@ -467,73 +463,69 @@ k_gradk_fft(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
   if (total == 0)
     for (int o = tid; o < 3 * K * FFT_N; o += C::THREADS) part[size_t(blockIdx.x) * 3 * K * FFT_N + o] = make_float2(0.f, 0.f);
 
-  // ---- deterministic two-level reduction over CTAs (whoever arrives last does the fixed-order sum) ----
-  __shared__ bool last;
-  const int ngroups = (gridDim.x + C::GROUP - 1) / C::GROUP;
-  const int grp = blockIdx.x / C::GROUP;
-  const int g0 = grp * C::GROUP, g1 = min(int(gridDim.x), g0 + C::GROUP);
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) last = (atomicAdd(&tickets[grp], 1u) == unsigned(g1 - g0 - 1));
-  __syncthreads();
-  if (!last) return;
-  __threadfence();
-  for (int o = tid; o < 3 * K * FFT_N; o += C::THREADS) {
-    double sx = 0.0, sy = 0.0;
-    for (int b = g0; b < g1; ++b) {
-      const float2 v = __ldcg(part + size_t(b) * 3 * K * FFT_N + o);
-      sx += double(v.x);
-      sy += double(v.y);
+}
+
+// Cross-CTA reduction of the frequency-domain sums, fixed order (deterministic): block = 64 elements x 4 quarter
+// ranges of the CTA list; tot[o] = sum over CTAs of part[cta][o] in double.
+__global__ void __launch_bounds__(256)
+k_gradk_fft_reduce(const State* __restrict__ st, const float2* __restrict__ part, int nparts, int nelem,
+                   double2* __restrict__ tot) {
+  if (st->stop) return;
+  __shared__ double2 sh[4][64];
+  const int e = threadIdx.x & 63, qtr = threadIdx.x >> 6;
+  const int o = blockIdx.x * 64 + e;
+  const int per = (nparts + 3) / 4, b0 = qtr * per, b1 = min(nparts, b0 + per);
+  double ax[4] = {0, 0, 0, 0}, ay[4] = {0, 0, 0, 0};
+  if (o < nelem) {
+    int b = b0;
+    for (; b + 4 <= b1; b += 4) {
+      float2 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = __ldcg(part + size_t(b + j) * nelem + o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { ax[j] += double(v[j].x); ay[j] += double(v[j].y); }
     }
-    gpart[size_t(grp) * 3 * K * FFT_N + o] = make_double2(sx, sy);
-  }
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    tickets[grp] = 0u;
-    last = (atomicAdd(&tickets[ngroups], 1u) == unsigned(ngroups - 1));
-  }
-  __syncthreads();
-  if (!last) return;
-  __threadfence();
-  // final: sum the groups in order, untangle A[k] = (C[k] + conj(C[-k]))/2, inverse DFT at the K lags s = dx - P
-  double2* tot = gpart + size_t(ngroups) * 3 * K * FFT_N;      // scratch behind the group partials
-  for (int o = tid; o < 3 * K * FFT_N; o += C::THREADS) {
-    double sx = 0.0, sy = 0.0;
-    for (int gi = 0; gi < ngroups; ++gi) {
-      const double2 v = __ldcg(gpart + size_t(gi) * 3 * K * FFT_N + o);
-      sx += v.x;
-      sy += v.y;
+    for (; b < b1; ++b) {
+      const float2 v = __ldcg(part + size_t(b) * nelem + o);
+      ax[(b - b0) & 3] += double(v.x);
+      ay[(b - b0) & 3] += double(v.y);
     }
-    tot[o] = make_double2(sx, sy);
   }
-  __threadfence();
+  sh[qtr][e] = make_double2((ax[0] + ax[1]) + (ax[2] + ax[3]), (ay[0] + ay[1]) + (ay[2] + ay[3]));
   __syncthreads();
-  const int par = seq & 1;
-  // exp(+2 pi i m / 128) in double, once (the spectra buffers are free by now)
-  double2* tw64 = reinterpret_cast<double2*>(smem + C::U_BYTES + C::E_BYTES);
-  for (int m = tid; m < FFT_N; m += C::THREADS) {
+  if (qtr == 0 && o < nelem)
+    tot[o] = make_double2((sh[0][e].x + sh[1][e].x) + (sh[2][e].x + sh[3][e].x), (sh[0][e].y + sh[1][e].y) + (sh[2][e].y + sh[3][e].y));
+}
+
+// Final step, one CTA: untangle A[k] = (C[k] + conj(C[-k]))/2, K-lag inverse DFT in double -> gk_sum (and, with row
+// bands, publish this band's sums to every band).  tot: [c][dy][k]; scratch: same size.
+__global__ void __launch_bounds__(512)
+k_gradk_fft_final(const State* __restrict__ st, const double2* __restrict__ tot, double2* __restrict__ scratch, int K,
+                  double* __restrict__ gk_sum, CommPeers cp, int seq) {
+  if (st->stop) return;
+  __shared__ double2 tw64[FFT_N];
+  const int tid = threadIdx.x, P = K / 2;
+  for (int m = tid; m < FFT_N; m += blockDim.x) {
     double sn, cs;
     sincospi(2.0 * double(m) / double(FFT_N), &sn, &cs);
     tw64[m] = make_double2(cs, sn);
   }
-  // untangle once per (c, dy, k): A[k] = (C[k] + conj(C[-k])) / 2, stored back over tot (second half of the scratch)
-  double2* Aun = tot + size_t(3) * K * FFT_N;
-  for (int o = tid; o < 3 * K * FFT_N; o += C::THREADS) {
+  for (int o = tid; o < 3 * K * FFT_N; o += blockDim.x) {
     const int k = o & (FFT_N - 1);
     const double2 a = tot[o], b = tot[o - k + ((FFT_N - k) & (FFT_N - 1))];
-    Aun[o] = make_double2(0.5 * (a.x + b.x), 0.5 * (a.y - b.y));
+    scratch[o] = make_double2(0.5 * (a.x + b.x), 0.5 * (a.y - b.y));
   }
   __threadfence();
   __syncthreads();
-  for (int o = tid; o < 3 * K * K; o += C::THREADS) {
+  const int par = seq & 1;
+  for (int o = tid; o < 3 * K * K; o += blockDim.x) {
     const int c = o / (K * K), r = o - c * K * K;
     const int dy = r / K, dx = r - dy * K;
-    const int s = dx - C::P;
-    const double2* row = Aun + (size_t(c) * K + dy) * FFT_N;
+    const int s = dx - P;
+    const double2* row = scratch + (size_t(c) * K + dy) * FFT_N;
     double s0 = 0.0, s1 = 0.0;
     for (int k = 0; k < FFT_N; k += 2) {                                  // Re(A[k] e^{+2 pi i k s / N}), two chains
-      const double2 a0 = row[k], a1 = row[k + 1];
+      const double2 a0 = __ldcg(row + k), a1 = __ldcg(row + k + 1);
       const double2 w0 = tw64[(k * s) & (FFT_N - 1)], w1 = tw64[((k + 1) * s) & (FFT_N - 1)];
       s0 += a0.x * w0.x - a0.y * w0.y;
       s1 += a1.x * w1.x - a1.y * w1.y;
@@ -543,11 +535,10 @@ k_gradk_fft(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
     if (cp.nranks > 1)
       for (int rr = 0; rr < cp.nranks; ++rr) cp.peer[rr]->gk_val[par][cp.rank][o] = sum;
   }
-  if (cp.nranks > 1) __threadfence_system();
-  __syncthreads();
-  if (tid == 0) {
-    tickets[ngroups] = 0u;
-    if (cp.nranks > 1) {
+  if (cp.nranks > 1) {
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
       for (int rr = 0; rr < cp.nranks; ++rr) *reinterpret_cast<volatile int*>(&cp.peer[rr]->gk_flag[par][cp.rank]) = seq;
       __threadfence_system();
     }

@@ -75,11 +75,14 @@ WORKLOADS = {
 }
 
 
-def make_case(name: str, seed: int = 0, scale: float = 1.0, iterations: int | None = None) -> Case:
-    """Build a named workload; ``scale`` < 1 shrinks the frame (parity tests run reduced sizes)."""
+def make_case(name: str, seed: int = 0, scale: float = 1.0, iterations: int | None = None, shape=None) -> Case:
+    """Build a named workload; ``scale`` < 1 shrinks the frame (parity tests run reduced sizes), ``shape=(M, N)``
+    overrides the frame size (e.g. to time one row band of a sharded frame on a single GPU)."""
     M, N, K, builder, blind, iters = WORKLOADS[name]
     M = max(int(M * scale), 3 * K + 8)
     N = max(int(N * scale), 3 * K + 8)
+    if shape is not None:
+        M, N = int(shape[0]), int(shape[1])
     k_true = utils.stack3(builder())
     image, u0 = make_inputs(M, N, k_true, seed)
     psf0 = utils.stack3(utils.uniform_kernel(K)) if blind else k_true.copy()
