@@ -77,7 +77,6 @@ struct rltv_ctx {
   // row-FFT hybrid stencils (9 <= K <= 17): input boxes 128 x (96+K-1)
   CUtensorMap tm_u_fft{}, tm_err_fft{}, tm_u_gkfft{}, tm_err_gkfft{};
   float2* gkf_part = nullptr;   // k_gradk_fft: per-CTA frequency-domain sums
-  double2* gkf_gpart = nullptr; // cross-CTA totals + untangled spectra
   float2* wspec = nullptr;      // tap spectra [2][3][K][128]
   bool use_fft = false;         // forward blur / adjoint through k_conv_fft
   bool use_fft_gradk = false;   // PSF gradient through k_gradk_fft
@@ -277,7 +276,6 @@ int launch_gradk_fft_t(rltv_ctx* c) {
     CU(cudaFuncSetAttribute(k_gradk_fft<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     const int ntx = (c->g.Wu + C::TWO - 1) / C::TWO, nty = (c->g.own1 - c->g.own0 + C::TROWS - 1) / C::TROWS;
     if (c->peers.nranks > 1) c->gk_seq += 1;
-    const int nelem = 3 * K * FFT_N;
     {
       ProfScope p(c, F_GRADK);
       k_gradk_fft<K><<<c->gk_nparts, C::THREADS, C::SMEM_BYTES, c->stream>>>(c->tm_u_gkfft, c->tm_err_gkfft, c->g, c->st, c->gkf_part,
@@ -285,11 +283,8 @@ int launch_gradk_fft_t(rltv_ctx* c) {
     }
     {
       ProfScope p(c, F_GRADK);
-      k_gradk_fft_reduce<<<(nelem + 63) / 64, 256, 0, c->stream>>>(c->st, c->gkf_part, c->gk_nparts, nelem, c->gkf_gpart);
-    }
-    {
-      ProfScope p(c, F_GRADK);
-      k_gradk_fft_final<<<1, 512, 0, c->stream>>>(c->st, c->gkf_gpart, c->gkf_gpart + nelem, K, c->gk_sum, c->peers, c->gk_seq);
+      k_gradk_fft_finish<<<3 * K, 512, 0, c->stream>>>(c->st, c->gkf_part, c->gk_nparts, K, c->gk_sum, c->peers, c->gk_seq,
+                                                       c->counters + 2);
     }
     return RLTV_OK;
   } else {
@@ -656,7 +651,6 @@ int rltv_create_band(rltv_ctx** out, int32_t device, int32_t M, int32_t N, int32
   CU(cudaMalloc(&c->wspec, size_t(2) * 3 * MK * FFT_N * sizeof(float2)));
   {
     CU(cudaMalloc(&c->gkf_part, size_t(c->gk_nparts) * 3 * MK * FFT_N * sizeof(float2)));
-    CU(cudaMalloc(&c->gkf_gpart, size_t(2) * 3 * MK * FFT_N * sizeof(double2)));   // total + untangled
   }
   {
     // Row-FFT hybrid stencils (csrc/rltv_stencil_fft.cuh) for the FP32-bound sizes; RLTV_CONV=direct|fft overrides
@@ -689,7 +683,7 @@ int rltv_destroy(rltv_ctx* c) {
   for (auto p : f) cudaFree(p);
   double* d[] = {c->gk_sum, c->wa, c->wb, c->rowacc, c->rowsum};
   for (auto p : d) cudaFree(p);
-  cudaFree(c->Z); cudaFree(c->tw); cudaFree(c->st); cudaFree(c->counters); cudaFree(c->wspec); cudaFree(c->gkf_part); cudaFree(c->gkf_gpart);
+  cudaFree(c->Z); cudaFree(c->tw); cudaFree(c->st); cudaFree(c->counters); cudaFree(c->wspec); cudaFree(c->gkf_part);
   if (c->h_st) cudaFreeHost(c->h_st);
   if (c->h_poll) cudaFreeHost(c->h_poll);
   for (auto& e : c->poll_ev) if (e) cudaEventDestroy(e);

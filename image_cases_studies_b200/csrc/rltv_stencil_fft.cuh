@@ -465,72 +465,68 @@ k_gradk_fft(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
 
 }
 
-// Cross-CTA reduction of the frequency-domain sums, fixed order (deterministic): block = 64 elements x 4 quarter
-// ranges of the CTA list; tot[o] = sum over CTAs of part[cta][o] in double.
-__global__ void __launch_bounds__(256)
-k_gradk_fft_reduce(const State* __restrict__ st, const float2* __restrict__ part, int nparts, int nelem,
-                   double2* __restrict__ tot) {
+// Finish of the PSF gradient, one CTA per (channel, dy) row of frequency-domain sums, everything in double and in a
+// fixed order (deterministic):  sum the per-CTA partials -> untangle A[k] = (C[k] + conj(C[-k]))/2 (two real rows were
+// packed per complex FFT) -> K-lag inverse DFT -> gk_sum.  With row bands the last CTA raises the "published" flags.
+__global__ void __launch_bounds__(512)
+k_gradk_fft_finish(const State* __restrict__ st, const float2* __restrict__ part, int nparts, int K,
+                   double* __restrict__ gk_sum, CommPeers cp, int seq, unsigned* __restrict__ ticket) {
   if (st->stop) return;
-  __shared__ double2 sh[4][64];
-  const int e = threadIdx.x & 63, qtr = threadIdx.x >> 6;
-  const int o = blockIdx.x * 64 + e;
+  __shared__ double2 sh[4][FFT_N];
+  __shared__ double2 A[FFT_N];
+  __shared__ double2 tw64[FFT_N];
+  const int tid = threadIdx.x, k = tid & (FFT_N - 1), qtr = tid >> 7, P = K / 2;
+  const int row = blockIdx.x;                                  // c * K + dy
+  const size_t nelem = size_t(3) * K * FFT_N;
+  const float2* src = part + size_t(row) * FFT_N + k;
   const int per = (nparts + 3) / 4, b0 = qtr * per, b1 = min(nparts, b0 + per);
   double ax[4] = {0, 0, 0, 0}, ay[4] = {0, 0, 0, 0};
-  if (o < nelem) {
-    int b = b0;
-    for (; b + 4 <= b1; b += 4) {
-      float2 v[4];
+  int b = b0;
+  for (; b + 8 <= b1; b += 8) {
+    float2 v[8];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) v[j] = __ldcg(part + size_t(b + j) * nelem + o);
+    for (int j = 0; j < 8; ++j) v[j] = __ldcg(src + size_t(b + j) * nelem);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { ax[j] += double(v[j].x); ay[j] += double(v[j].y); }
-    }
-    for (; b < b1; ++b) {
-      const float2 v = __ldcg(part + size_t(b) * nelem + o);
-      ax[(b - b0) & 3] += double(v.x);
-      ay[(b - b0) & 3] += double(v.y);
-    }
+    for (int j = 0; j < 8; ++j) { ax[j & 3] += double(v[j].x); ay[j & 3] += double(v[j].y); }
   }
-  sh[qtr][e] = make_double2((ax[0] + ax[1]) + (ax[2] + ax[3]), (ay[0] + ay[1]) + (ay[2] + ay[3]));
-  __syncthreads();
-  if (qtr == 0 && o < nelem)
-    tot[o] = make_double2((sh[0][e].x + sh[1][e].x) + (sh[2][e].x + sh[3][e].x), (sh[0][e].y + sh[1][e].y) + (sh[2][e].y + sh[3][e].y));
-}
-
-// Final step, one CTA: untangle A[k] = (C[k] + conj(C[-k]))/2, K-lag inverse DFT in double -> gk_sum (and, with row
-// bands, publish this band's sums to every band).  tot: [c][dy][k]; scratch: same size.
-__global__ void __launch_bounds__(512)
-k_gradk_fft_final(const State* __restrict__ st, const double2* __restrict__ tot, double2* __restrict__ scratch, int K,
-                  double* __restrict__ gk_sum, CommPeers cp, int seq) {
-  if (st->stop) return;
-  __shared__ double2 tw64[FFT_N];
-  const int tid = threadIdx.x, P = K / 2;
-  for (int m = tid; m < FFT_N; m += blockDim.x) {
+  for (; b < b1; ++b) {
+    const float2 v = __ldcg(src + size_t(b) * nelem);
+    ax[(b - b0) & 3] += double(v.x);
+    ay[(b - b0) & 3] += double(v.y);
+  }
+  sh[qtr][k] = make_double2((ax[0] + ax[1]) + (ax[2] + ax[3]), (ay[0] + ay[1]) + (ay[2] + ay[3]));
+  if (tid < FFT_N) {
     double sn, cs;
-    sincospi(2.0 * double(m) / double(FFT_N), &sn, &cs);
-    tw64[m] = make_double2(cs, sn);
+    sincospi(2.0 * double(tid) / double(FFT_N), &sn, &cs);
+    tw64[tid] = make_double2(cs, sn);
   }
-  for (int o = tid; o < 3 * K * FFT_N; o += blockDim.x) {
-    const int k = o & (FFT_N - 1);
-    const double2 a = tot[o], b = tot[o - k + ((FFT_N - k) & (FFT_N - 1))];
-    scratch[o] = make_double2(0.5 * (a.x + b.x), 0.5 * (a.y - b.y));
-  }
-  __threadfence();
   __syncthreads();
-  const int par = seq & 1;
-  for (int o = tid; o < 3 * K * K; o += blockDim.x) {
-    const int c = o / (K * K), r = o - c * K * K;
-    const int dy = r / K, dx = r - dy * K;
+  if (tid < FFT_N)
+    sh[0][k] = make_double2((sh[0][k].x + sh[1][k].x) + (sh[2][k].x + sh[3][k].x), (sh[0][k].y + sh[1][k].y) + (sh[2][k].y + sh[3][k].y));
+  __syncthreads();
+  if (tid < FFT_N) {
+    const double2 a = sh[0][k], c = sh[0][(FFT_N - k) & (FFT_N - 1)];
+    A[k] = make_double2(0.5 * (a.x + c.x), 0.5 * (a.y - c.y));
+  }
+  __syncthreads();
+  // lag dx - P by 16 threads: 8 bins each, then a fixed xor tree
+  const int dx = tid >> 4, j = tid & 15;
+  double acc = 0.0;
+  if (dx < K) {
     const int s = dx - P;
-    const double2* row = scratch + (size_t(c) * K + dy) * FFT_N;
-    double s0 = 0.0, s1 = 0.0;
-    for (int k = 0; k < FFT_N; k += 2) {                                  // Re(A[k] e^{+2 pi i k s / N}), two chains
-      const double2 a0 = __ldcg(row + k), a1 = __ldcg(row + k + 1);
-      const double2 w0 = tw64[(k * s) & (FFT_N - 1)], w1 = tw64[((k + 1) * s) & (FFT_N - 1)];
-      s0 += a0.x * w0.x - a0.y * w0.y;
-      s1 += a1.x * w1.x - a1.y * w1.y;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int kk = j * 8 + i;
+      const double2 a = A[kk], w = tw64[(kk * s) & (FFT_N - 1)];
+      acc += a.x * w.x - a.y * w.y;                            // Re(A[k] e^{+2 pi i k s / N})
     }
-    const double sum = (s0 + s1) * (1.0 / double(FFT_N));
+  }
+#pragma unroll
+  for (int m = 1; m < 16; m <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+  const int par = seq & 1;
+  if (dx < K && j == 0) {
+    const double sum = acc * (1.0 / double(FFT_N));
+    const int o = row * K + dx;
     gk_sum[o] = sum;
     if (cp.nranks > 1)
       for (int rr = 0; rr < cp.nranks; ++rr) cp.peer[rr]->gk_val[par][cp.rank][o] = sum;
@@ -538,7 +534,9 @@ k_gradk_fft_final(const State* __restrict__ st, const double2* __restrict__ tot,
   if (cp.nranks > 1) {
     __threadfence_system();
     __syncthreads();
-    if (tid == 0) {
+    if (tid == 0 && atomicAdd(ticket, 1u) == gridDim.x - 1) {
+      *ticket = 0u;
+      __threadfence_system();
       for (int rr = 0; rr < cp.nranks; ++rr) *reinterpret_cast<volatile int*>(&cp.peer[rr]->gk_flag[par][cp.rank]) = seq;
       __threadfence_system();
     }
