@@ -2,14 +2,15 @@
 // One inner step of the reference (lib/deconvolution.pyx:473-591) is the kernel sequence
 //   GRAD     : k_conv<K,fwd> -> k_conv<K,adj>                         (pyx:477-491, :519, :524)
 //   UPDATE   : k_update [-> k_halo_push]                              (pyx:527-531, :499-502, :552)
-//   PSF_GRAD : [k_halo_wait ->] k_conv<K,fwd> -> k_gradk<K> -> reduce (pyx:557-571)
+//   PSF_GRAD : k_conv<K,fwd> -> k_gradk<K> -> reduce                  (pyx:557-571)
 //   PSF_STEP : k_psf_update                                           (pyx:574-589)
 // and one outer iteration (pyx:460-656) is  ut=u ; 5 inner steps ; whiteness statistic + stop rule.
 // Nothing is read back between kernels: step sizes, the PSF, the statistic and the stop flag live in a
 // device-resident State; once the flag is set every later kernel returns at its first instruction, so the
 // host may run ahead (it polls the flag two outer iterations behind, without draining the stream).
-// With row-band sharding (one context per GPU) the host all-reduces three tiny device buffers between
-// phases (step_max, gk_sum, stop); halos move by peer stores inside k_halo_push.
+// With row-band sharding (one context per GPU, rltv_band.cuh) halos, step scalars, PSF-gradient sums and the stop
+// flag cross GPUs by peer stores from inside these same kernels; the NCCL-baseline mode instead steps phase by
+// phase and lets the host-side caller all-reduce three tiny device buffers (step_max, gk_sum, stop).
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -90,7 +91,6 @@ struct rltv_ctx {
   unsigned* counters = nullptr; // [0] halo push, [1] adjoint, [2] gradk "last CTA" tickets
   int halo_seq = 0;             // exchange numbers: identical on every band, never reset
   int max_seq = 0, gk_seq = 0, stop_seq = 0;
-  bool halo_pending = false;    // a push has been issued since the last wait
   bool white_owner = true;
   bool ignore_stop = false;     // benchmark stepping only: evaluate the stop rule, do not act on it
   int outer_since_begin = 0;
@@ -360,19 +360,10 @@ int launch_psf_update(rltv_ctx* c) {
 int launch_halo_push(rltv_ctx* c) {
   if (!c->side[0].peer_u && !c->side[1].peer_u) return RLTV_OK;
   c->halo_seq += 1;
-  c->halo_pending = true;
-  ProfScope p(c, F_HALO);
-  k_halo_push<<<2 * c->num_sms, 256, 0, c->stream>>>(c->g, c->st, c->u, c->side[0], c->side[1], c->counters + 0, c->halo_seq);
-  return RLTV_OK;
-}
-
-int launch_halo_wait(rltv_ctx* c) {
-  if (!c->halo_pending) return RLTV_OK;
-  c->halo_pending = false;
   const int* flags = reinterpret_cast<const Comm*>(reinterpret_cast<const char*>(c->u) + c->flag_offset)->halo_flag;
   ProfScope p(c, F_HALO);
-  k_halo_wait<<<1, 32, 0, c->stream>>>(c->st, c->side[0].peer_u ? flags + 0 : nullptr,
-                                       c->side[1].peer_u ? flags + 1 : nullptr, c->halo_seq);
+  k_halo_push<<<2 * c->num_sms, 256, 0, c->stream>>>(c->g, c->st, c->u, c->side[0], c->side[1], c->counters + 0, c->halo_seq,
+                                                     c->side[0].peer_u ? flags + 0 : nullptr, c->side[1].peer_u ? flags + 1 : nullptr);
   return RLTV_OK;
 }
 
@@ -474,25 +465,18 @@ int enqueue_phase(rltv_ctx* c, int phase) {
   int rc = RLTV_OK;
   switch (phase) {
     case RLTV_PH_OUTER_BEGIN: {
-      if ((rc = launch_halo_wait(c)) != RLTV_OK) return rc;       // ut must copy refreshed halos
       ProfScope p(c, F_COPY);                                      // ut[:] = u.copy(), pyx:462
       CU(cudaMemcpyAsync(c->ut, c->u, 3 * c->g.plane * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
       return RLTV_OK;
     }
     case RLTV_PH_GRAD:
-      if ((rc = launch_halo_wait(c)) != RLTV_OK) return rc;
       if ((rc = launch_conv_fwd(c)) != RLTV_OK) return rc;        // pyx:477-488
       if ((rc = launch_conv_adj(c, c->params.lambd)) != RLTV_OK) return rc;   // pyx:490-491, :519, :524
-      if (c->peers.nranks > 1) {
-        ProfScope p(c, F_HALO);
-        k_stepmax_gather<<<1, 32, 0, c->stream>>>(c->st, c->peers.peer[c->rank], c->peers.nranks, c->max_seq);
-      }
       return RLTV_OK;
     case RLTV_PH_UPDATE:
       if ((rc = launch_update(c)) != RLTV_OK) return rc;          // pyx:527-531, :499-502, :552
       return launch_halo_push(c);
     case RLTV_PH_PSF_GRAD:
-      if ((rc = launch_halo_wait(c)) != RLTV_OK) return rc;
       if ((rc = launch_conv_fwd(c)) != RLTV_OK) return rc;        // pyx:557-565
       return launch_gradk(c);                                     // pyx:567-571
     case RLTV_PH_PSF_STEP:
@@ -749,7 +733,6 @@ int rltv_download_rows(rltv_ctx* c, float* u, size_t u_rs, int32_t row0, int32_t
     if (u_rs < size_t(g.Wu) * 12) return fail(RLTV_ERR_ARG, "u row stride smaller than a packed row");
     const int l0 = row0 - g.row0;
     if (l0 < 0 || l0 + nrows > g.Hu) return fail(RLTV_ERR_ARG, "rows not held by this band");
-    if (c->halo_pending) { if ((rc = launch_halo_wait(c)) != RLTV_OK) return rc; }
     k_planar_to_hwc<<<dim3(hwc_grid(g.Wu), nrows), 256, 0, c->stream>>>(c->u, g, l0, 0, nrows, g.Wu, c->staging, size_t(g.Wu) * 3);
     c->launches++;
     CU(cudaMemcpy2DAsync(u, u_rs, c->staging, size_t(g.Wu) * 12, size_t(g.Wu) * 12, nrows, cudaMemcpyDeviceToHost, c->stream));

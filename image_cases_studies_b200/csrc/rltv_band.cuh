@@ -4,9 +4,9 @@
 //
 //   halo exchange   after the update kernel rewrote the owned rows of u (lib/deconvolution.pyx:527-531, :552)
 //                   each band pushes its first / last 2P owned rows into the bottom / top halo of its
-//                   neighbours (k_halo_push); the next reader of u is preceded by k_halo_wait;
+//                   neighbours (k_halo_push) and the same kernel ends only when the neighbours' rows have landed;
 //   step scalars    the last CTA of the adjoint kernel publishes the band's max(u_c), max|G_c| (pyx:524) into slot
-//                   [rank] of EVERY band's Comm block; k_stepmax_gather waits for all slots and takes the max;
+//                   [rank] of EVERY band's Comm block, then waits for all slots and takes the max;
 //   PSF gradient    the last CTA of k_gradk sums the per-CTA partials (double, fixed order) and publishes the
 //                   band's 3*K*K sums (pyx:571); k_psf_update waits for all bands and adds them in rank order, so
 //                   every band computes the bit-identical PSF without a broadcast;
@@ -59,7 +59,7 @@ __device__ __forceinline__ void spin_until(const int* flag, int seq) {
 // grid-stride float4 copy of nrows x pitch x 3 planes to each neighbour, then (last CTA) raise the flags.
 __global__ void __launch_bounds__(256)
 k_halo_push(Geom g, const State* __restrict__ st, const float* __restrict__ u, HaloSide top, HaloSide bot,
-            unsigned* __restrict__ done_counter, int seq) {
+            unsigned* __restrict__ done_counter, int seq, const int* flag_from_top, const int* flag_from_bot) {
   if (st->stop) return;
   const int row4 = g.pitch / 4;
   const HaloSide sides[2] = {top, bot};
@@ -86,14 +86,13 @@ k_halo_push(Geom g, const State* __restrict__ st, const float* __restrict__ u, H
     if (bot.peer_u) *reinterpret_cast<volatile int*>(bot.peer_flag) = seq;
     __threadfence_system();
   }
-}
-
-// One warp: lanes 0/1 spin until the neighbours' pushes number `seq` have landed in this band's halo rows.
-__global__ void k_halo_wait(const State* __restrict__ st, const int* flag_from_top, const int* flag_from_bot, int seq) {
-  if (st->stop) return;
-  const int* f = threadIdx.x == 0 ? flag_from_top : (threadIdx.x == 1 ? flag_from_bot : nullptr);
-  if (f) spin_until(f, seq);
-  __threadfence_system();
+  // ... and the kernel does not end before the neighbours' pushes number `seq` have landed in this band's halo rows:
+  // the next reader of u simply follows in stream order.  (A neighbour's push never waits for this kernel.)
+  if (last && threadIdx.x < 2) {
+    const int* f = threadIdx.x == 0 ? flag_from_top : flag_from_bot;
+    if (f) spin_until(f, seq);
+    __threadfence_system();
+  }
 }
 
 // Called by ONE thread of the last CTA of the adjoint kernel: publish this band's step scalars to every band.
@@ -115,10 +114,11 @@ __device__ __forceinline__ void publish_step_max(State* st, const CommPeers& cp,
   __threadfence_system();
 }
 
-// One warp: wait for every band's scalars of step `seq`, reduce with max into the local State (pyx:524).
-__global__ void k_stepmax_gather(State* __restrict__ st, Comm* __restrict__ mine, int nranks, int seq) {
-  if (st->stop) return;
-  const int par = seq & 1, lane = threadIdx.x;
+// Warp 0 of the last CTA of the adjoint kernel, right after publish_step_max: wait for every band's scalars of step
+// `seq` and reduce them with max into the local State (pyx:524).  No band's publication depends on this wait, so
+// there is no cycle; the update kernel that follows in stream order sees the global maxima.
+__device__ __forceinline__ void gather_step_max(State* st, Comm* mine, int nranks, int seq, int lane) {
+  const int par = seq & 1;
   if (lane < nranks) spin_until(&mine->max_flag[par][lane], seq);
   __syncwarp();
   __threadfence_system();
@@ -127,6 +127,24 @@ __global__ void k_stepmax_gather(State* __restrict__ st, Comm* __restrict__ mine
     for (int r = 0; r < nranks; ++r) m = max(m, *reinterpret_cast<volatile int*>(&mine->max_val[par][r][lane]));
     if (lane < 3) st->max_u[lane] = m; else st->max_G[lane - 3] = m;
   }
+}
+
+// Tail of the adjoint kernels with row bands: the last CTA to finish publishes this band's step scalars to every band
+// (peer stores) and gathers everybody's.  `slot` is one free word of shared memory; call with all threads.
+__device__ __forceinline__ void band_step_max_tail(State* st, const CommPeers& cp, int seq, unsigned* done_counter, int* slot) {
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int last = (atomicAdd(done_counter, 1u) == gridDim.x - 1);
+    if (last) {
+      *done_counter = 0u;
+      __threadfence();
+      publish_step_max(st, cp, seq);
+    }
+    *slot = last;
+  }
+  __syncthreads();
+  if (*slot && threadIdx.x < 32) gather_step_max(st, cp.peer[cp.rank], cp.nranks, seq, threadIdx.x);
 }
 
 // Non-owning bands: wait for the stop decision of outer iteration `seq` from the band that holds the window.

@@ -278,18 +278,7 @@ k_conv(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtens
       }
     }
   }
-  if (ADJ && cp.nranks > 1) {
-    // row bands: the last CTA to finish publishes this band's step scalars to every band (peer stores)
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-      if (atomicAdd(done_counter, 1u) == gridDim.x - 1) {
-        *done_counter = 0u;
-        __threadfence();
-        publish_step_max(st, cp, seq);
-      }
-    }
-  }
+  if (ADJ && cp.nranks > 1) band_step_max_tail(st, cp, seq, done_counter, reinterpret_cast<int*>(smem));
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -294,17 +294,7 @@ k_conv_fft(const __grid_constant__ CUtensorMap tm_in, const float* __restrict__ 
   }
   if (tid == 0)
     for (int i = 0; i < 6; ++i) atomicAdd(&g_fft_phase_cycles[i], (unsigned long long)ph[i]);
-  if (ADJ && cp.nranks > 1) {
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-      if (atomicAdd(done_counter, 1u) == gridDim.x - 1) {
-        *done_counter = 0u;
-        __threadfence();
-        publish_step_max(st, cp, seq);
-      }
-    }
-  }
+  if (ADJ && cp.nranks > 1) band_step_max_tail(st, cp, seq, done_counter, reinterpret_cast<int*>(smem));
 }
 
 }  // namespace rltv
