@@ -356,8 +356,9 @@ k_gradk_fft(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
   uint64_t* bar = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(tw) + FFT_N * 8);
   const int tid = threadIdx.x;
   const int tiles_per_c = ntx * nty;
-  const int my_tiles = (tiles_per_c > int(blockIdx.x)) ? (tiles_per_c - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x) : 0;
-  const int total = 3 * my_tiles;
+  // tiles of all three channels form one list dealt round-robin to the CTAs (no per-channel rounding up)
+  const int all_tiles = 3 * tiles_per_c;
+  const int total = (all_tiles > int(blockIdx.x)) ? (all_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x) : 0;
 
   if (tid == 0) {
     mbar_init(bar, 1);
@@ -369,7 +370,8 @@ k_gradk_fft(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
   __syncthreads();
 
   auto issue = [&](int q) {
-    const int c = q / my_tiles, tl = blockIdx.x + (q - c * my_tiles) * gridDim.x;
+    const int f = blockIdx.x + q * gridDim.x;
+    const int c = f / tiles_per_c, tl = f - c * tiles_per_c;
     const int by = tl / ntx, bx = tl - by * ntx;
     mbar_arrive_expect_tx(bar, C::U_BYTES + C::E_BYTES);
     tma_load_3d(smem, &tm_u, bx * C::TWO - C::P4, g.own0 + by * C::TROWS - C::P, c, bar);
@@ -381,6 +383,7 @@ k_gradk_fft(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
 #pragma unroll
   for (int d = 0; d < K; ++d) acc[d] = make_float2(0.f, 0.f);
 
+  unsigned flushed = 0u;                              // channels this CTA wrote a partial for (CTA-uniform)
   if (tid == 0 && total > 0) issue(0);
   for (int q = 0; q < total; ++q) {
     mbar_wait(bar, q & 1);
@@ -427,8 +430,9 @@ k_gradk_fft(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
       }
     }
     __syncthreads();      // ZU / ZE are free for the next tile
-    const int c = q / my_tiles;
-    if (q + 1 == total || (q + 1) / my_tiles != c) {
+    const int c = (blockIdx.x + q * gridDim.x) / tiles_per_c;
+    if (q + 1 == total || int(blockIdx.x + (q + 1) * gridDim.x) / tiles_per_c != c) {
+      flushed |= 1u << c;
       // end of a channel: fold the row chunks (fixed order) through the spectra buffers and write this CTA's partial
       float2* red = ZU;   // [chunk][K][128]
 #pragma unroll
@@ -450,9 +454,9 @@ k_gradk_fft(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
       __syncthreads();
     }
   }
-  if (total == 0)
-    for (int o = tid; o < 3 * K * FFT_N; o += C::THREADS) part[size_t(blockIdx.x) * 3 * K * FFT_N + o] = make_float2(0.f, 0.f);
-
+  for (int c = 0; c < 3; ++c)                         // channels this CTA had no tile of
+    if (!(flushed & (1u << c)))
+      for (int o = tid; o < K * FFT_N; o += C::THREADS) part[(size_t(blockIdx.x) * 3 + c) * K * FFT_N + o] = make_float2(0.f, 0.f);
 }
 
 // Finish of the PSF gradient, one CTA per (channel, dy) row of frequency-domain sums, everything in double and in a
@@ -481,8 +485,8 @@ k_gradk_fft_finish(const State* __restrict__ st, const float2* __restrict__ part
   }
   for (; b < b1; ++b) {
     const float2 v = __ldcg(src + size_t(b) * nelem);
-    ax[(b - b0) & 3] += double(v.x);
-    ay[(b - b0) & 3] += double(v.y);
+    ax[0] += double(v.x);
+    ay[0] += double(v.y);
   }
   sh[qtr][k] = make_double2((ax[0] + ax[1]) + (ax[2] + ax[3]), (ay[0] + ay[1]) + (ay[2] + ay[3]));
   if (tid < FFT_N) {
