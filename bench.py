@@ -50,6 +50,17 @@ FAMILY_BYTES_PER_PX = {"conv_fwd": 24.0,   # read u, image (residual consumed on
                        "gradk": 12.0}      # read u (residual on chip)
 
 
+def ncu_traffic(workload, family):
+    """DRAM bytes per launch of `family` from the committed ncu --set full capture of this workload (else None)."""
+    p = ROOT / "profiles" / "ncu_traffic_r01.json"
+    if not p.exists():
+        return None, None
+    d = json.loads(p.read_text())
+    if d.get("workload") != workload:
+        return None, None
+    return d["per_launch_dram_bytes"].get(family), f"profiles/{p.name} ({d.get('source')})"
+
+
 def peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -353,8 +364,10 @@ def main():
     flops_launch = 2.0 * 3 * K * K * M * N * rows_frac
     step_bytes = BYTES_PER_PX_STEP[case.blind] * M * N * INNER
     ms_step = ms / args.steps
+    # measured DRAM traffic of the same kernel: only meaningful for the whole frame on one GPU at the profiled size
+    traffic, traffic_src = (ncu_traffic(case.name, dom) if (world == 1 and not args.frame and args.scale == 1.0) else (None, None))
     roofline = {"bound": "hbm", "kernel": f"{dom}<{K}>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": dom_ms,
                 "share_of_step": fam_tot[dom] / tot,
                 # FLOPs of the DIRECT K x K stencil (2*3*K*K per pixel).  For 11 <= K <= 17 the kernels evaluate it through

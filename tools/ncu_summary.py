@@ -14,13 +14,34 @@ KEYS = [("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "dram_rd"),
         ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem_conflicts"), ("lts__t_bytes.sum", "l2_bytes")]
 
 
-def main(rep):
+FAMILIES = [("k_conv_fft<", ", 0>", "conv_fwd"), ("k_conv_fft<", ", 1>", "conv_adj"), ("k_conv<", ", 0>", "conv_fwd"),
+            ("k_conv<", ", 1>", "conv_adj"), ("k_update", "", "update"), ("k_gradk_fft<", "", "gradk"), ("k_gradk<", "", "gradk")]
+
+
+def to_bytes(val, unit):
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    return float(val.replace(",", "")) * scale[unit]
+
+
+def family_of(name):
+    for a, b, fam in FAMILIES:
+        if a in name and (not b or b in name.split("(")[0]):
+            return fam
+    return None
+
+
+def main(rep, json_out=None, workload=None):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units, data = rows[0], rows[1], rows[2:]
     idx = {h: i for i, h in enumerate(hdr)}
     stall = [h for h in hdr if "issue_stalled" in h and h.endswith("per_issue_active.ratio")]
+    traffic = {}
     for d in data:
+        fam = family_of(d[idx["Kernel Name"]])
+        if fam and "dram__bytes_read.sum" in idx:
+            rd, wr = idx["dram__bytes_read.sum"], idx["dram__bytes_write.sum"]
+            traffic.setdefault(fam, []).append(to_bytes(d[rd], units[rd]) + to_bytes(d[wr], units[wr]))
         print("kernel:", d[idx["Kernel Name"]][:90])
         for k, short in KEYS:
             if k in idx:
@@ -31,5 +52,14 @@ def main(rep):
         print()
 
 
+    if json_out:
+        import json
+        json.dump({"workload": workload, "source": rep.split("/")[-1],
+                   "what": "dram__bytes_read.sum + dram__bytes_write.sum per launch (mean over the captured launches), ncu --set full",
+                   "per_launch_dram_bytes": {f: sum(v) / len(v) for f, v in traffic.items()},
+                   "launches_captured": {f: len(v) for f, v in traffic.items()}}, open(json_out, "w"), indent=1)
+
+
 if __name__ == "__main__":
-    main(sys.argv[1])
+    # ncu_summary.py REPORT [JSON_OUT WORKLOAD]
+    main(*sys.argv[1:4])
