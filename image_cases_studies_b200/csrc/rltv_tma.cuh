@@ -56,6 +56,13 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* t
       : "memory");
 }
 
+// Warm L2 with a box that a later tma_load_3d will fetch (no shared-memory destination, no completion to wait for).
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* tmap, int x, int y, int c) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(x), "r"(y), "r"(c)
+               : "memory");
+}
+
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
 }
