@@ -17,8 +17,8 @@ steps, as BASELINE.md defines it:  value = M*N*5*steps / seconds / 1e6.
                on the bounded crop).
 
 N > 1 (torchrun, one rank per GPU): the SAME frame is split into row bands, one per GPU (strong scaling):
-halo rows move by peer stores over NVLink, the step scalars / PSF gradient / stop flag by NCCL all-reduce
-(image_cases_studies_b200/distributed.py); device time is the max over ranks.
+halo rows, step scalars, PSF-gradient sums and the stop flag all move by in-kernel peer stores over NVLink
+(image_cases_studies_b200/distributed.py; `--comm nccl` = host all-reduce baseline); device time is the max over ranks.
 """
 from __future__ import annotations
 
@@ -168,7 +168,7 @@ def run_reference_impl(args):
         return
     r = cpu_reference_sample(args.workload, args.steps, args.warmup)
     if r is None:
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref (compiled reference) not present"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref (compiled reference) not present"})
         return
     line = {"metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
@@ -177,7 +177,7 @@ def run_reference_impl(args):
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------------------
@@ -240,13 +240,29 @@ def run_frame_batch(args, rank, dev, world):
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": img_h.nbytes + u_h.nbytes + psf_h.nbytes,
                         "d2h_bytes_per_step": u_h.nbytes},
                 "roofline": None, "cpu_baseline": None, "gpu_launches": int(launches)}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
 # --------------------------------------------------------------------------------------------------------
+def emit(line):
+    """The ONE JSON line of the contract, on the real stdout (see main: fd 1 is parked on stderr while running)."""
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(line), flush=True)
+
+
+_REAL_STDOUT = None
+
+
 def main():
+    # libraries (NCCL's version banner, torchrun notices) write to fd 1: keep stdout for the JSON line alone
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -448,7 +464,7 @@ def main():
                            "stop_rule": "evaluated every step, not acted upon in the timed region (obeyed in e2e)"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_timed,
                 "clocks": clocks.summary()}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
