@@ -7,7 +7,7 @@
 //                   neighbours (k_halo_push) and the same kernel ends only when the neighbours' rows have landed;
 //   step scalars    the last CTA of the adjoint kernel publishes the band's max(u_c), max|G_c| (pyx:524) into slot
 //                   [rank] of EVERY band's Comm block, then waits for all slots and takes the max;
-//   PSF gradient    the last CTA of k_gradk sums the per-CTA partials (double, fixed order) and publishes the
+//   PSF gradient    the last CTA of k_gradk / k_gradk_fft_finish sums the per-CTA partials (double, fixed order) and publishes the
 //                   band's 3*K*K sums (pyx:571); k_psf_update waits for all bands and adds them in rank order, so
 //                   every band computes the bit-identical PSF without a broadcast;
 //   stop flag       the band holding the whiteness window publishes the stop decision (pyx:643-654).

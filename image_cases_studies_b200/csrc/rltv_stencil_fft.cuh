@@ -309,7 +309,7 @@ namespace rltv {
 //   frequency domain over all rows and all tiles:   C[dy][k] += conj(Ze[y][k]) Zu[y+dy][k].
 //   Rows are packed in pairs like in k_conv_fft (Z = row y + i row y+HB); the packed product equals A + iB with
 //   A = conj(E)U + conj(E')U' (wanted) and B a cross term; both are spectra of real sequences, hence
-//   A[k] = (C[k] + conj(C[-k])) / 2 -- untangled once, by the last CTA, before a 15-lag inverse DFT in double.
+//   A[k] = (C[k] + conj(C[-k])) / 2 -- untangled once, by k_gradk_fft_finish, before a K-lag inverse DFT in double.
 // Per 80 x 112 tile (K <= 17; 64 x 96 above): forward row FFTs + HB*128*K complex MACs; no inverse FFT, no epilogue.
 // One real-data stage only: the next tile's TMA is issued as soon as the forward FFTs have consumed the stage and
 // overlaps the MAC phase.
@@ -339,7 +339,7 @@ struct GradkFftCfg {
   static_assert(SMEM_BYTES <= 227 * 1024, "does not fit shared memory");
 };
 
-// part: [cta][c][dy][k] float2 per-CTA frequency-domain sums; k_gradk_fft_reduce / k_gradk_fft_final finish the job
+// part: [cta][c][dy][k] float2 per-CTA frequency-domain sums; k_gradk_fft_finish does the rest
 template <int K>
 __global__ void __launch_bounds__(GradkFftCfg<K>::THREADS, 1)
 k_gradk_fft(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_e, Geom g,

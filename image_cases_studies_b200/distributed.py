@@ -5,10 +5,11 @@ The padded estimate ``u`` is cut into contiguous row bands; each band also holds
 its neighbours.  Per inner step (lib/deconvolution.pyx:473-591):
 
     GRAD      forward blur + adjoint on the band; the adjoint kernel's last CTA publishes the band's
-              max(u_c), max|G_c| (pyx:524) into every band's memory; a one-warp kernel gathers the max
-    UPDATE    gradient step + blend, then the band PUSHES its edge rows into the neighbours' halos
-    PSF_GRAD  wait for the neighbours' flags, residual, PSF-gradient partial sums; the last CTA publishes the
-              band's 3*MK*MK sums (pyx:571) to every band
+              max(u_c), max|G_c| (pyx:524) into every band's memory, then waits for everybody's and takes the max
+    UPDATE    gradient step + blend, then the band PUSHES its edge rows into the neighbours' halos; the push
+              kernel ends when the neighbours' rows have landed here too
+    PSF_GRAD  residual, PSF-gradient partial sums; the finishing CTA publishes the band's 3*MK*MK sums
+              (pyx:571) to every band
     PSF_STEP  waits for all bands' sums, adds them in rank order, identical tiny update on every rank
               (the replicated PSF stays bit-identical without a broadcast)
 
