@@ -73,6 +73,35 @@ def test_stages_against_oracle(K):
         assert rel_l2(gk[..., c], gk_ref) < 5e-5
 
 
+@pytest.mark.parametrize("K", [3, 9, 15, 31])
+@pytest.mark.parametrize("shape", [(1, 1), (2, 3), (17, 5), (47, 113), (48, 112), (49, 111), (97, 225)])
+def test_stages_tiny_and_tile_edge_shapes(K, shape):
+    """Frames smaller than one tile, exactly one tile, one pixel past a tile (direct tiles: 16 x 128, row-FFT tiles:
+    48 x 112 / 64 x 96): every kernel alone against the float64 definition, K on both sides of the direct/FFT switch."""
+    from image_cases_studies_b200.solver import Solver
+    from oracle import rl_mm_oracle as orc
+    M, N = shape
+    rng = np.random.default_rng(1000 * K + 10 * M + N)
+    u = rng.random((M + K - 1, N + K - 1, 3), dtype=np.float32)
+    image = rng.random((M, N, 3), dtype=np.float32)
+    psf = rng.random((K, K, 3), dtype=np.float32)
+    psf /= psf.sum(axis=(0, 1), keepdims=True)
+    s = Solver(M, N, K)
+    s.upload(image, u, psf)
+    err = s.stage_residual()
+    g = s.stage_adjoint()
+    gk = s.stage_gradk()
+    s.close()
+    assert err.shape == (M, N, 3) and g.shape == u.shape and gk.shape == (K, K, 3)
+    for c in range(3):
+        e_ref = orc.conv2(u[..., c], psf[..., c], "valid") - image[..., c]
+        assert rel_l2(err[..., c], e_ref) < 5e-6
+        g_ref = orc.conv2(e_ref, orc.rot180(psf[..., c]), "full")
+        assert rel_l2(g[..., c], g_ref) < 5e-6
+        gk_ref = orc.conv2(orc.rot180(u[..., c]), e_ref, "valid")
+        assert rel_l2(gk[..., c], gk_ref) < 5e-5
+
+
 @pytest.mark.parametrize("win", [(4, 60, 4, 60), (3, 120, 10, 97), (0, 33, 5, 200)])
 def test_whiteness_statistic(win):
     from image_cases_studies_b200.solver import Solver
