@@ -368,9 +368,13 @@ def main():
     fam_tot = {f: t for f, (t, n) in prof.items()}
     tot = sum(fam_tot.values()) or 1.0
     dom = max(("conv_fwd", "conv_adj", "update", "gradk"), key=lambda f: fam_tot.get(f, 0.0))
-    alg_bytes = FAMILY_BYTES_PER_PX[dom] * M * N * rows_frac
-    # the row-FFT PSF gradient is two launches (accumulate + finish) timed under one family: report them per gradient
     conv_mode = os.environ.get("RLTV_CONV", "fft" if K >= 11 else "direct")
+    fused_residual = case.blind and conv_mode == "fft" and K <= 17 and os.environ.get("RLTV_FUSE", "1") != "0"
+    fam_bytes = dict(FAMILY_BYTES_PER_PX)
+    if fused_residual:
+        fam_bytes["gradk"] = 24.0        # the PSF-gradient kernel computes the residual itself: reads u and the image
+    alg_bytes = fam_bytes[dom] * M * N * rows_frac
+    # the row-FFT PSF gradient is two launches (accumulate + finish) timed under one family: report them per gradient
     gk_launches = 2 if conv_mode == "fft" else 1
     if prof["gradk"][1]:
         fam_ms["gradk"] = fam_tot["gradk"] / max(prof["gradk"][1] // gk_launches, 1)

@@ -78,6 +78,7 @@ SYMBOLS = [
     ("rltv_stage_residual", C.c_int, [C.c_void_p, C.c_void_p]),
     ("rltv_stage_adjoint", C.c_int, [C.c_void_p, C.c_void_p]),
     ("rltv_stage_gradk", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("rltv_debug_download_err", C.c_int, [C.c_void_p, C.c_void_p]),
     ("rltv_stage_tv", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]),
     ("rltv_debug_phase_cycles", C.c_int, [C.POINTER(C.c_uint64)]),
     ("rltv_debug_fft128", C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),

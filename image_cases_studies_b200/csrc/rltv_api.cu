@@ -77,10 +77,13 @@ struct rltv_ctx {
   CUtensorMap tm_u_conv{}, tm_err_conv{}, tm_img_epi{}, tm_u_epi{}, tm_ut_epi{}, tm_u_gk{}, tm_err_gk{};
   // row-FFT hybrid stencils (9 <= K <= 17): input boxes 128 x (96+K-1)
   CUtensorMap tm_u_fft{}, tm_err_fft{}, tm_u_gkfft{}, tm_err_gkfft{};
+  CUtensorMap tm_img_gkfft;     // image rows of the owned rows, same boxes as tm_err_gkfft (fused residual)
   float2* gkf_part = nullptr;   // k_gradk_fft: per-CTA frequency-domain sums
   float2* wspec = nullptr;      // tap spectra [2][3][K][128]
   bool use_fft = false;         // forward blur / adjoint through k_conv_fft
   bool use_fft_gradk = false;   // PSF gradient through k_gradk_fft
+  bool fuse_residual = false;   // ... which also computes the residual of pyx:557-565 itself (no forward-blur launch)
+  bool psf_grad_write_err = true;  // fused kernel stores the residual (needed by the whiteness statistic only)
   double* gk_sum = nullptr;
   // row bands: halo exchange + all-gathers through peer memory (rltv_band.cuh)
   HaloSide side[2]{};           // 0: band above, 1: band below
@@ -210,6 +213,7 @@ int make_maps_t(rltv_ctx* c) {
     using GF = GradkFftCfg<K>;
     if ((rc = make_tmap(&c->tm_u_gkfft, c->u, g, g.Hu, FFT_N, GF::U_ROWS))) return rc;
     if ((rc = make_tmap(&c->tm_err_gkfft, c->err + size_t(g.own0) * g.pitch, g, g.own1 - g.own0, FFT_N, GF::TROWS))) return rc;
+    if ((rc = make_tmap(&c->tm_img_gkfft, c->img + size_t(g.own0) * g.pitch, g, g.own1 - g.own0, FFT_N, GF::TROWS))) return rc;
   }
   return RLTV_OK;
 }
@@ -273,13 +277,23 @@ template <int K>
 int launch_gradk_fft_t(rltv_ctx* c) {
   if constexpr (K >= 9) {
     using C = GradkFftCfg<K>;
-    CU(cudaFuncSetAttribute(k_gradk_fft<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    CU(cudaFuncSetAttribute(k_gradk_fft<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     const int ntx = (c->g.Wu + C::TWO - 1) / C::TWO, nty = (c->g.own1 - c->g.own0 + C::TROWS - 1) / C::TROWS;
     if (c->peers.nranks > 1) c->gk_seq += 1;
     {
       ProfScope p(c, F_GRADK);
-      k_gradk_fft<K><<<c->gk_nparts, C::THREADS, C::SMEM_BYTES, c->stream>>>(c->tm_u_gkfft, c->tm_err_gkfft, c->g, c->st, c->gkf_part,
-                                                                           ntx, nty);
+      bool fused = false;
+      if constexpr (C::CAN_FUSE) {
+        if (c->fuse_residual) {
+          fused = true;
+          CU(cudaFuncSetAttribute(k_gradk_fft<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES_FUSED));
+          k_gradk_fft<K, true><<<c->gk_nparts, C::THREADS, C::SMEM_BYTES_FUSED, c->stream>>>(
+              c->tm_u_gkfft, c->tm_img_gkfft, c->g, c->st, c->wspec, c->psf_grad_write_err ? c->err : nullptr, c->gkf_part, ntx, nty);
+        }
+      }
+      if (!fused)
+        k_gradk_fft<K, false><<<c->gk_nparts, C::THREADS, C::SMEM_BYTES, c->stream>>>(c->tm_u_gkfft, c->tm_err_gkfft, c->g, c->st,
+                                                                                    nullptr, nullptr, c->gkf_part, ntx, nty);
     }
     {
       ProfScope p(c, F_GRADK);
@@ -380,7 +394,8 @@ int setup_whiteness(rltv_ctx* c, int top, int bottom, int left, int right) {
     return fail(RLTV_ERR_ARG, "whiteness window outside the image");
   if (c->white_owner) {
     const int l0 = top + c->g.P - c->g.row0, l1 = bottom + c->g.P - c->g.row0;
-    if (l0 < c->fwd0 || l1 > c->fwd1)
+    const int r0 = c->fuse_residual ? c->g.own0 : c->fwd0, r1 = c->fuse_residual ? c->g.own1 : c->fwd1;
+    if (l0 < r0 || l1 > r1)
       return fail(RLTV_ERR_ARG, "whiteness window is not inside the rows this band computes the residual on");
   }
   const int mx = h > w ? h : w;
@@ -477,7 +492,8 @@ int enqueue_phase(rltv_ctx* c, int phase) {
       if ((rc = launch_update(c)) != RLTV_OK) return rc;          // pyx:527-531, :499-502, :552
       return launch_halo_push(c);
     case RLTV_PH_PSF_GRAD:
-      if ((rc = launch_conv_fwd(c)) != RLTV_OK) return rc;        // pyx:557-565
+      if (!c->fuse_residual)
+        if ((rc = launch_conv_fwd(c)) != RLTV_OK) return rc;      // pyx:557-565 (else inside the PSF-gradient kernel)
       return launch_gradk(c);                                     // pyx:567-571
     case RLTV_PH_PSF_STEP:
       return launch_psf_update(c);                                // pyx:574-589
@@ -507,7 +523,11 @@ int enqueue_outer(rltv_ctx* c) {
     if ((rc = enqueue_phase(c, RLTV_PH_GRAD)) != RLTV_OK) return rc;
     if ((rc = enqueue_phase(c, RLTV_PH_UPDATE)) != RLTV_OK) return rc;
     if (c->params.blind) {
-      if ((rc = enqueue_phase(c, RLTV_PH_PSF_GRAD)) != RLTV_OK) return rc;
+      // only the last residual of an outer iteration is read again (by the whiteness statistic, pyx:623-638)
+      c->psf_grad_write_err = (i == RLTV_INNER_ITER - 1);
+      rc = enqueue_phase(c, RLTV_PH_PSF_GRAD);
+      c->psf_grad_write_err = true;
+      if (rc != RLTV_OK) return rc;
       if ((rc = enqueue_phase(c, RLTV_PH_PSF_STEP)) != RLTV_OK) return rc;
     }
   }
@@ -643,6 +663,8 @@ int rltv_create_band(rltv_ctx** out, int32_t device, int32_t M, int32_t N, int32
     if (e && !strcmp(e, "direct")) c->use_fft = false;
     if (e && !strcmp(e, "fft") && MK >= 9) c->use_fft = true;
     c->use_fft_gradk = c->use_fft;
+    c->fuse_residual = c->use_fft_gradk && MK <= 17;             // GradkFftCfg<K>::CAN_FUSE
+    if (const char* e = getenv("RLTV_FUSE")) c->fuse_residual = c->fuse_residual && atoi(e) != 0;
   }
   {
     int rc = make_maps(c);
@@ -982,6 +1004,18 @@ int rltv_stage_adjoint(rltv_ctx* c, float* g_out) {
     k_planar_to_hwc<<<dim3(8, g.Hu), 256, 0, c->stream>>>(c->gbuf, g, 0, 0, g.Hu, g.Wu, c->staging, size_t(g.Wu) * 3);
     CU(cudaMemcpyAsync(g_out, c->staging, size_t(g.Hu) * g.Wu * 12, cudaMemcpyDeviceToHost, c->stream));
   }
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  return RLTV_OK;
+}
+
+int rltv_debug_download_err(rltv_ctx* c, float* err_out) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  if (!c->uploaded || c->banded || !err_out) return fail(RLTV_ERR_STATE, "needs an uploaded whole-frame context");
+  const Geom& g = c->g;
+  k_planar_to_hwc<<<dim3(8, g.M), 256, 0, c->stream>>>(c->err, g, g.P, g.P, g.M, g.N, c->staging, size_t(g.N) * 3);
+  CU(cudaMemcpyAsync(err_out, c->staging, size_t(g.M) * g.N * 12, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaGetLastError());
   return RLTV_OK;

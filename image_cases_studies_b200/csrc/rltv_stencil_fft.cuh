@@ -332,6 +332,10 @@ struct GradkFftCfg {
   static constexpr int ZU_BYTES = ZU_ROWS * FFT_PITCH * 8;
   static constexpr int ZE_BYTES = HB * FFT_PITCH * 8;
   static constexpr int SMEM_BYTES = U_BYTES + E_BYTES + ZU_BYTES + ZE_BYTES + FFT_N * 8 + 64 + 128;
+  // fused variant (residual computed in the kernel): + the forward tap spectra of the current channel
+  static constexpr int WS_BYTES = K * FFT_N * 8;
+  static constexpr int SMEM_BYTES_FUSED = SMEM_BYTES + WS_BYTES;
+  static constexpr bool CAN_FUSE = (SMEM_BYTES_FUSED <= 227 * 1024) && (CHUNK % 2 == 0);
   static_assert(NCH * CHUNK == HB, "row chunks cover the packed rows");
   static_assert(NCH * K * FFT_N * 8 <= ZU_BYTES + ZE_BYTES, "chunk-reduction scratch fits the spectra buffers");
   static_assert(P4 + TWO - 1 + P <= FFT_N - 1, "segment too short for this K");
@@ -339,12 +343,21 @@ struct GradkFftCfg {
   static_assert(SMEM_BYTES <= 227 * 1024, "does not fit shared memory");
 };
 
-// part: [cta][c][dy][k] float2 per-CTA frequency-domain sums; k_gradk_fft_finish does the rest
-template <int K>
+// part: [cta][c][dy][k] float2 per-CTA frequency-domain sums; k_gradk_fft_finish does the rest.
+//
+// FUSED = true computes the residual of pyx:557-565 in the same kernel instead of reading it: the u rows it needs
+// are exactly the rows whose spectra this kernel already holds, so the separate forward-blur launch (its TMA loads,
+// its forward FFTs, its residual write and this kernel's read of it) disappears.  tm_e then maps the IMAGE, and per
+// tile   Ze <- FFT( mask( IFFT( sum_ky W[ky] Zu[y+ky] ) - image ) )   (vertical MAC, inverse FFT, residual, forward FFT:
+// the same steps as k_conv_fft<K,false>, whose results it reproduces), optionally stored to err_out for the whiteness
+// statistic (pyx:623-638 reads the residual of the last inner step).
+template <int K, bool FUSED>
 __global__ void __launch_bounds__(GradkFftCfg<K>::THREADS, 1)
 k_gradk_fft(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_e, Geom g,
-            const State* __restrict__ st, float2* __restrict__ part, int ntx, int nty) {
+            const State* __restrict__ st, const float2* __restrict__ wspec, float* __restrict__ err_out,
+            float2* __restrict__ part, int ntx, int nty) {
   using C = GradkFftCfg<K>;
+  static_assert(!FUSED || C::CAN_FUSE, "fused residual does not fit for this K");
   if (st->stop) return;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
@@ -354,6 +367,7 @@ k_gradk_fft(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
   float2* ZE = reinterpret_cast<float2*>(smem + C::U_BYTES + C::E_BYTES + C::ZU_BYTES);
   float2* tw = reinterpret_cast<float2*>(smem + C::U_BYTES + C::E_BYTES + C::ZU_BYTES + C::ZE_BYTES);
   uint64_t* bar = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(tw) + FFT_N * 8);
+  float2* WS = reinterpret_cast<float2*>(smem + C::SMEM_BYTES - 128);   // FUSED only: forward tap spectra [K][128]
   const int tid = threadIdx.x;
   const int tiles_per_c = ntx * nty;
   // tiles of all three channels form one list dealt round-robin to the CTAs (no per-channel rounding up)
@@ -394,31 +408,124 @@ k_gradk_fft(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
   for (int d = 0; d < K; ++d) acc[d] = make_float2(0.f, 0.f);
 
   unsigned flushed = 0u;                              // channels this CTA wrote a partial for (CTA-uniform)
+  int cur_c = -1;
+  const int nown = g.own1 - g.own0;
   if (tid == 0 && total > 0) issue(0);
   for (int q = 0; q < total; ++q) {
     if (tid == 0 && q + 1 < total) prefetch(q + 1);
+    if constexpr (FUSED) {
+      const int c = (blockIdx.x + q * gridDim.x) / tiles_per_c;
+      if (c != cur_c) {                               // forward tap spectra of this channel (WS is idle between tiles)
+        const float2* wsrc = wspec + size_t(c) * K * FFT_N;
+        for (int i = tid; i < K * FFT_N; i += C::THREADS) WS[i] = __ldg(wsrc + i);
+        cur_c = c;
+      }
+    }
     mbar_wait(bar, q & 1);
     __syncwarp();
-    // forward FFTs: packed u rows, then packed err rows (columns outside the 112 valid ones are zeroed)
-    for (int task = tid; task < (C::ZU_ROWS + C::HB) * 8; task += C::THREADS) {
-      const unsigned mask = __activemask();
-      const int zr = task >> 3, tt = task & 7;
-      if (zr < C::ZU_ROWS) {
+    if constexpr (!FUSED) {
+      // forward FFTs: packed u rows, then packed err rows (columns outside the 112 valid ones are zeroed)
+      for (int task = tid; task < (C::ZU_ROWS + C::HB) * 8; task += C::THREADS) {
+        const unsigned mask = __activemask();
+        const int zr = task >> 3, tt = task & 7;
+        if (zr < C::ZU_ROWS) {
+          const float* ra = uR + zr * FFT_N;
+          const float* rb = uR + (zr + C::HB) * FFT_N;
+          fft128_row<false>(ZU + zr * FFT_PITCH, tw, tt, [&](int n) { return make_float2(ra[n], rb[n]); }, mask, zr & 3);
+        } else {
+          const int er = zr - C::ZU_ROWS;
+          const float* ra = eR + er * FFT_N;
+          const float* rb = eR + (er + C::HB) * FFT_N;
+          fft128_row<false>(ZE + er * FFT_PITCH, tw, tt, [&](int n) {
+            const bool in = (n >= C::P4) && (n < C::P4 + C::TWO);
+            return in ? make_float2(ra[n], rb[n]) : make_float2(0.f, 0.f);
+          }, mask, zr & 3);
+        }
+      }
+      __syncthreads();
+      if (tid == 0 && q + 1 < total) issue(q + 1);    // the real-data stage is free: overlap the load with the MAC
+    } else {
+      const int f = blockIdx.x + q * gridDim.x;
+      const int c = f / tiles_per_c, tl = f - c * tiles_per_c;
+      const int by = tl / ntx, bx = tl - by * ntx;
+      // a. forward FFT of the packed u rows
+      for (int task = tid; task < C::ZU_ROWS * 8; task += C::THREADS) {
+        const unsigned mask = __activemask();
+        const int zr = task >> 3, tt = task & 7;
         const float* ra = uR + zr * FFT_N;
         const float* rb = uR + (zr + C::HB) * FFT_N;
         fft128_row<false>(ZU + zr * FFT_PITCH, tw, tt, [&](int n) { return make_float2(ra[n], rb[n]); }, mask, zr & 3);
-      } else {
-        const int er = zr - C::ZU_ROWS;
-        const float* ra = eR + er * FFT_N;
-        const float* rb = eR + (er + C::HB) * FFT_N;
-        fft128_row<false>(ZE + er * FFT_PITCH, tw, tt, [&](int n) {
-          const bool in = (n >= C::P4) && (n < C::P4 + C::TWO);
-          return in ? make_float2(ra[n], rb[n]) : make_float2(0.f, 0.f);
-        }, mask, zr & 3);
       }
+      __syncthreads();
+      // b. blur: O[y][bin] = sum_ky Wc[ky][bin] Zu[y + ky][bin] -> ZE row y, two half-chunks to stay within registers
+      {
+        constexpr int HC = C::CHUNK / 2;
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          const int y0 = chunk * C::CHUNK + half * HC;
+          float2 z[HC + K - 1];
+#pragma unroll
+          for (int i = 0; i < HC + K - 1; ++i) z[i] = ZU[(y0 + i) * FFT_PITCH + bin];
+          float2 o[HC];
+#pragma unroll
+          for (int y = 0; y < HC; ++y) o[y] = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int ky = 0; ky < K; ++ky) {
+            const float2 w = WS[ky * FFT_N + bin];
+#pragma unroll
+            for (int y = 0; y < HC; ++y) {
+              o[y].x = fmaf(w.x, z[y + ky].x, o[y].x);
+              o[y].x = fmaf(-w.y, z[y + ky].y, o[y].x);
+              o[y].y = fmaf(w.x, z[y + ky].y, o[y].y);
+              o[y].y = fmaf(w.y, z[y + ky].x, o[y].y);
+            }
+          }
+#pragma unroll
+          for (int y = 0; y < HC; ++y) ZE[(y0 + y) * FFT_PITCH + bin] = o[y];
+        }
+      }
+      __syncthreads();
+      // c. back to the signal domain: real part = blurred row y, imaginary part = blurred row y + HB
+      for (int task = tid; task < C::HB * 8; task += C::THREADS) {
+        const unsigned mask = __activemask();
+        const int zr = task >> 3, tt = task & 7;
+        float2* row = ZE + zr * FFT_PITCH;
+        fft128_row<true>(row, tw, tt, [&](int n) { return row[n]; }, mask);
+      }
+      __syncthreads();
+      // d. residual = blur - image inside the image and the owned rows, zero elsewhere (and in the 16 invalid columns)
+      {
+        const int x0 = bx * C::TWO - C::P4;
+        for (int i = tid; i < C::HB * FFT_N; i += C::THREADS) {
+          const int r = i >> 7, n = i & (FFT_N - 1);
+          const float2 v = ZE[r * FFT_PITCH + n];
+          const int X = x0 + n;
+          const bool nvalid = (n >= C::P4) && (n < C::P4 + C::TWO);
+          const bool colin = nvalid && X >= C::P && X < C::P + g.N;
+          float e[2];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int rl = by * C::TROWS + r + h * C::HB;          // row inside the owned rows
+            const int gy = g.row0 + g.own0 + rl;                   // row of the padded frame
+            const bool ok = colin && rl < nown && gy >= C::P && gy < C::P + g.M;
+            e[h] = ok ? (h ? v.y : v.x) - eR[(r + h * C::HB) * FFT_N + n] : 0.f;
+            if (err_out != nullptr && nvalid && X < g.pitch && rl < nown)
+              err_out[size_t(c) * g.plane + size_t(g.own0 + rl) * g.pitch + X] = e[h];
+          }
+          ZE[r * FFT_PITCH + n] = make_float2(e[0], e[1]);
+        }
+      }
+      __syncthreads();
+      if (tid == 0 && q + 1 < total) issue(q + 1);    // u and image rows are consumed: reload under the phases below
+      // e. spectra of the packed residual rows
+      for (int task = tid; task < C::HB * 8; task += C::THREADS) {
+        const unsigned mask = __activemask();
+        const int zr = task >> 3, tt = task & 7;
+        float2* row = ZE + zr * FFT_PITCH;
+        fft128_row<false>(row, tw, tt, [&](int n) { return row[n]; }, mask);
+      }
+      __syncthreads();
     }
-    __syncthreads();
-    if (tid == 0 && q + 1 < total) issue(q + 1);      // the real-data stage is free: overlap the load with the MAC
     // MAC: C[dy][bin] += conj(Ze[y][bin]) * Zu[y + dy][bin]; a K-deep register window slides down the packed u rows
     {
       const float2* zu0 = ZU + (chunk * C::CHUNK) * FFT_PITCH + bin;

@@ -40,7 +40,8 @@ def plan_bands(M: int, MK: int, world: int, window=None):
     Returns ``(bands, owner)``: bands[r] = (row_lo, row_hi, own_lo, own_hi) in frame rows, ``owner`` the rank
     whose band evaluates the whiteness statistic for ``window = (top, bottom, left, right)`` (image rows).
     Every band owns >= 2P rows (halos come from the immediate neighbours only); the window must lie inside the
-    rows on which its owner computes the residual (owned rows +- P), so a cut is moved below the window if needed.
+    rows its owner OWNS (the fused PSF-gradient kernel leaves the residual of the owned rows only), so a cut is
+    moved below the window if needed.
     """
     P = MK // 2
     Hu = M + MK - 1
@@ -51,12 +52,12 @@ def plan_bands(M: int, MK: int, world: int, window=None):
     if window is not None and world > 1:
         wt, wb = window[0] + P, window[1] + P            # window rows in u coordinates
         owner = max(i for i in range(world) if cuts[i] <= wt)
-        if owner < world - 1 and wb > cuts[owner + 1] + P:
-            cuts[owner + 1] = wb - P                      # move the cut below the window ...
+        if owner < world - 1 and wb > cuts[owner + 1]:
+            cuts[owner + 1] = wb                          # move the cut below the window ...
             rest = world - (owner + 1)                    # ... and re-balance the bands after it
             for j in range(1, rest):
                 cuts[owner + 1 + j] = cuts[owner + 1] + round(j * (Hu - cuts[owner + 1]) / rest)
-        if owner > 0 and wt < cuts[owner] - P:
+        if wt < cuts[owner] or wb > cuts[owner + 1]:
             raise ValueError("whiteness window straddles a band boundary")
     bands = []
     for r in range(world):

@@ -163,6 +163,12 @@ class Solver:
         nat.check(nat.lib.rltv_stage_gradk(self._ctx, nat.ptr(out)))
         return out
 
+    def debug_residual(self) -> np.ndarray:
+        """The residual buffer currently on the device (whatever kernel wrote it last)."""
+        out = np.empty((self.M, self.N, 3), np.float32)
+        nat.check(nat.lib.rltv_debug_download_err(self._ctx, nat.ptr(out)))
+        return out
+
     def stage_tv(self, order: int, norm: int, epsilon: float):
         """TV norm map and divergence of the device-resident estimate (lib/deconvolution.pyx:137-239)."""
         out = np.empty(self.u_shape, np.float32)

@@ -159,8 +159,12 @@ int rltv_poll_wait(rltv_ctx* ctx, int32_t it, int32_t* stop);
 int rltv_stage_residual(rltv_ctx* ctx, float* err_out /* packed HWC (M,N,3) */);
 /* g = full-conv(err, rot180(psf)) on the u domain (pyx:490-491), using the residual currently on device */
 int rltv_stage_adjoint(rltv_ctx* ctx, float* g_out /* packed HWC (M+MK-1, N+MK-1, 3) */);
-/* gk = valid-conv(rot180(u), err) (pyx:567-571) using the residual currently on device */
+/* gk = valid-conv(rot180(u), err) (pyx:567-571).  Direct kernels / MK > 17: uses the residual currently on device
+ * (call rltv_stage_residual first).  Row-FFT kernels, MK <= 17: the kernel computes the residual of pyx:557-565
+ * itself from u, psf and the image and leaves it on the device (read it with rltv_debug_download_err). */
 int rltv_stage_gradk(rltv_ctx* ctx, float* gk_out /* packed (MK,MK,3) */);
+/* debug: the residual buffer currently on the device, packed HWC (M, N, 3) */
+int rltv_debug_download_err(rltv_ctx* ctx, float* err_out);
 /* TV(u, out, M, N, epsilon, order, norm, div) (pyx:137-239) of the estimate on the device; order, norm in {1,2};
  * out/div: packed HWC (M+MK-1, N+MK-1, 3), zero on the border ring; *ms = device time of the stencil kernel */
 int rltv_stage_tv(rltv_ctx* ctx, int32_t order, int32_t norm, float epsilon, float* out, float* div, float* ms);

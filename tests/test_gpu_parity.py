@@ -280,6 +280,43 @@ def test_fft128_engine(inverse):
     assert np.abs(out - ref).max() <= 2e-5 * np.abs(ref).max()
 
 
+@pytest.mark.parametrize("K", [9, 11, 13, 15, 17])
+def test_fused_residual_in_psf_gradient_kernel(K, monkeypatch):
+    """k_gradk_fft<K, FUSED>: the PSF-gradient kernel that computes the residual of pyx:557-565 itself (no forward-blur
+    launch before it), and the residual it leaves behind for the whiteness statistic, against (a) the two-kernel
+    sequence it replaces (RLTV_FUSE=0: same arithmetic, so nearly bit-equal) and (b) the float64 definition."""
+    from image_cases_studies_b200.solver import Solver
+    from oracle import rl_mm_oracle as orc
+    monkeypatch.setenv("RLTV_CONV", "fft")
+    rng = np.random.default_rng(100 + K)
+    M, N = 171 + K, 233 + 2 * K           # ragged against the 80 x 112 tiles
+    u = (0.1 + 0.8 * rng.random((M + K - 1, N + K - 1, 3))).astype(np.float32)
+    psf = rng.random((K, K, 3), dtype=np.float32)
+    psf /= psf.sum(axis=(0, 1), keepdims=True)
+    # a blurred scene plus a small perturbation: the residual is small and zero-mean like in the solver
+    image = np.stack([orc.conv2(u[..., c], psf[..., c], "valid") for c in range(3)], axis=2)
+    image = (image * (1.0 + 0.05 * rng.standard_normal(image.shape))).astype(np.float32)
+    res = {}
+    for fuse in ("1", "0"):
+        monkeypatch.setenv("RLTV_FUSE", fuse)
+        s = Solver(M, N, K)
+        s.upload(image, u, psf)
+        if fuse == "0":
+            s.stage_residual()
+        gk = s.stage_gradk()
+        res[fuse] = (gk, s.debug_residual())
+        s.close()
+    assert rel_l2(res["1"][1], res["0"][1]) < 1e-5, "residual left by the fused kernel vs k_conv_fft"
+    assert rel_l2(res["1"][0], res["0"][0]) < 1e-4, "PSF gradient, fused vs two kernels"
+    for c in range(3):
+        e_ref = orc.conv2(u[..., c], psf[..., c], "valid") - image[..., c]
+        gk_ref = orc.conv2(orc.rot180(u[..., c]), e_ref, "valid")
+        for fuse in ("1", "0"):
+            assert rel_l2(res[fuse][1][..., c], e_ref) < 1e-4, f"residual vs float64, RLTV_FUSE={fuse}"
+            # zero-mean residual against a DC-heavy estimate: the fp32 row spectra bound this at a few 1e-4
+            assert rel_l2(res[fuse][0][..., c], gk_ref) < 1e-3, f"PSF gradient vs float64, RLTV_FUSE={fuse}"
+
+
 @pytest.mark.parametrize("K", [9, 11, 13, 15, 17, 19, 25, 31])
 def test_row_fft_stencils_against_oracle(K, monkeypatch):
     """k_conv_fft (row-FFT hybrid forward blur / adjoint, csrc/rltv_stencil_fft.cuh) against the float64 definition."""
