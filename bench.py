@@ -137,28 +137,42 @@ def pinned(a: np.ndarray) -> np.ndarray:
 
 
 # --------------------------------------------------------------------------------------------------------
-def cpu_reference_sample(workload: str, steps: int, warmup: int):
-    """Times the reference's compiled solver (oracle/_ref) on a bounded crop: one step = one outer iteration."""
+def cpu_reference_sample(workload: str, steps: int, warmup: int, force_port: bool = False):
+    """Times the reference's CPU implementation on a bounded crop: one step = one outer iteration.
+
+    kind "reference": the reference's own compiled solver (oracle/_ref, all host cores through its OpenMP loops);
+    kind "port": the numpy restatement (oracle/rl_mm_oracle.py, float32) when oracle/_ref is not present."""
     from image_cases_studies_b200 import synthetic
     from oracle import ref_loader
-    if ref_loader.load() is None:
-        return None
+    have_ref = (not force_port) and ref_loader.load() is not None
     _, _, K, _, blind, _ = synthetic.WORKLOADS[workload]
-    M, N = 600, 900
-    full_M, full_N = synthetic.WORKLOADS[workload][:2]
+    M = 600 if have_ref else 300
+    full_M = synthetic.WORKLOADS[workload][0]
     c = synthetic.make_case(workload, seed=0, scale=min(1.0, M / full_M), iterations=1)
     M, N = c.shape
+    if have_ref:
+        def one():
+            ref_loader.run(c.image, c.u0, c.psf0, c.window, c.tau, 1, c.step_factor, c.lambd, c.blind)
+    else:
+        from oracle import rl_mm_oracle
+
+        def one():
+            rl_mm_oracle.richardson_lucy_MM(c.image, c.u0, c.psf0, *c.window, c.tau, M, N, 3, c.MK, 1, c.step_factor,
+                                            c.lambd, blind=c.blind, dtype=np.float32)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        ref_loader.run(c.image, c.u0, c.psf0, c.window, c.tau, 1, c.step_factor, c.lambd, c.blind)
+        one()
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
     total = sum(times)
-    return {"value": M * N * INNER * len(times) / total / 1e6, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
+    how = ("the reference's compiled solver; throughput per pixel is size-independent: it convolves by FFT" if have_ref
+           else "numpy port of the reference algorithm, single thread")
+    return {"value": M * N * INNER * len(times) / total / 1e6, "unit": UNIT, "cores": os.cpu_count() if have_ref else 1,
+            "kind": "reference" if have_ref else "port",
             "sample": f"{M}x{N} crop of {workload}, MK={K}, {'blind' if blind else 'non-blind'}, {len(times)} outer iteration(s) "
-                      f"of 5 inner steps each (throughput per pixel is size-independent: the reference convolves by FFT)",
+                      f"of 5 inner steps each ({how})",
             "seconds": total, "ms_per_step": 1e3 * total / len(times)}
 
 
@@ -167,9 +181,6 @@ def run_reference_impl(args):
     if rank != 0:
         return
     r = cpu_reference_sample(args.workload, args.steps, args.warmup)
-    if r is None:
-        emit({"impl": "reference", "unavailable": "oracle/_ref (compiled reference) not present"})
-        return
     line = {"metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
