@@ -1,7 +1,7 @@
 """Generate tests/golden/*.npz by running the REFERENCE'S OWN compiled solver (oracle/_ref).
 
 Run in the build container (where /root/reference exists and `python oracle/build_ref.py` has
-produced oracle/_ref):      python tests/golden/make_golden.py
+produced oracle/_ref):      python tests/golden/make_golden.py [--force]
 
 Each fixture holds the exact float32 inputs handed to ``richardson_lucy_MM``
 (lib/deconvolution.pyx:341) and what the unmodified reference returned / mutated: the output view,
@@ -63,6 +63,19 @@ CASES = {
                        dict(tau=0.0, iterations=5, step_factor=5e-3, lambd=5e3, blind=True)),
     "blind_80x64_k15": (lambda: white_case(80, 64, 15, utils.gaussian_kernel(15, 3.0), True, 15),
                         dict(tau=0.0, iterations=2, step_factor=1e-3, lambd=1e4, blind=True)),
+    # K >= 11: the row-FFT stencils (and, up to 17, the fused residual + PSF-gradient kernel) are the default path
+    "blind_96x120_k11": (lambda: white_case(96, 120, 11, utils.gaussian_kernel(11, 2.5), True, 21),
+                         dict(tau=0.0, iterations=3, step_factor=1e-3, lambd=1e4, blind=True)),
+    "blind_corr_88x104_k13": (lambda: white_case(88, 104, 13, utils.kaiser_kernel(13, 5.0), True, 22),
+                              dict(tau=0.0, iterations=3, step_factor=1e-3, lambd=1e4, blind=True, correlation=True)),
+    "blind_100x90_k17": (lambda: white_case(100, 90, 17, utils.gaussian_kernel(17, 3.5), True, 23),
+                         dict(tau=0.0, iterations=2, step_factor=1e-3, lambd=1e4, blind=True)),
+    "nonblind_90x110_k15": (lambda: white_case(90, 110, 15, utils.gaussian_kernel(15, 3.0), False, 24),
+                            dict(tau=1.0, iterations=3, step_factor=1e-3, lambd=1e4, blind=False)),
+    "blind_96x96_k25": (lambda: white_case(96, 96, 25, utils.gaussian_kernel(25, 5.0), True, 25),
+                        dict(tau=0.0, iterations=2, step_factor=1e-3, lambd=1e4, blind=True)),
+    "blind_100x100_k31": (lambda: white_case(100, 100, 31, utils.gaussian_kernel(31, 6.0), True, 26),
+                          dict(tau=0.0, iterations=2, step_factor=1e-3, lambd=1e4, blind=True)),
     "nonblind_stop_80x96_k7": (lambda: smooth_case(80, 96, 7, False, 0),
                                dict(tau=0.0, iterations=30, step_factor=1e-3, lambd=1e4, blind=False)),
     "nonblind_stop2_80x96_k7": (lambda: smooth_case(80, 96, 7, False, 1),
@@ -74,7 +87,11 @@ def main():
     mod = ref_loader.load()
     if mod is None:
         sys.exit("oracle/_ref missing: run python oracle/build_ref.py first")
+    force = "--force" in sys.argv
     for name, (builder, kw) in CASES.items():
+        if (OUT / f"{name}.npz").exists() and not force:      # committed fixtures are only rewritten with --force
+            print(f"{name}: kept")
+            continue
         image, u0, psf0, window = builder()
         out, u, psf, log = ref_loader.run(image, u0, psf0, window, kw["tau"], kw["iterations"], kw["step_factor"],
                                           kw["lambd"], kw["blind"], kw.get("correlation", False))
@@ -84,6 +101,8 @@ def main():
                             lambd=kw["lambd"], blind=kw["blind"], correlation=kw.get("correlation", False),
                             ref_out=np.ascontiguousarray(out), ref_u=u, ref_psf=psf, ref_iterations=its)
         print(f"{name}: executed {its}/{kw['iterations']} outer iterations, out {out.shape}")
+    if (OUT / "normalize_kernel_k7.npz").exists() and not force:
+        return
     # normalize_kernel (lib/deconvolution.pyx:73-75) on a kernel with negative taps
     rng = np.random.default_rng(21)
     kern = (rng.random((7, 7, 3), dtype=np.float32) - 0.3).astype(np.float32)
