@@ -69,7 +69,8 @@ k_psf_spectrum(const State* __restrict__ st, const float* __restrict__ psf, int 
 }
 
 // Per-phase cycle counters of k_conv_fft (thread 0 of every CTA; read by rltv_debug_phase_cycles): 0 wait for the
-// TMA tile, 1 forward FFT, 2 MAC (+ operand prefetch), 3 inverse FFT, 4 epilogue, 5 statistics flush.
+// TMA tile, 1 forward FFT, 2 MAC (+ operand prefetch), 3 inverse FFT, 4 epilogue, 5 statistics flush.  Only filled
+// by a -DRLTV_PHASE_PROBE build; the clock reads are not ordered against the barriers, so the split is approximate.
 __device__ unsigned long long g_fft_phase_cycles[8];
 
 template <int K, bool ADJ>
@@ -117,8 +118,14 @@ k_conv_fft(const __grid_constant__ CUtensorMap tm_in, const float* __restrict__ 
   if (tid == 0 && t < ntiles) issue_in(t);
   int cur_c = -1;
   float mu = -INFINITY, mG = 0.f;
+  // phase probe (tools/phase_probe.py): compiled in only with -DRLTV_PHASE_PROBE -- its six 64-bit counters cost the
+  // production kernel 88 bytes of register spills at the 80-register cap of two 384-thread CTAs per SM
+#ifdef RLTV_PHASE_PROBE
   long long ph[6] = {0, 0, 0, 0, 0, 0}, tprev = clock64();
   auto mark = [&](int i) { if (tid == 0) { const long long now = clock64(); ph[i] += now - tprev; tprev = now; } };
+#else
+  auto mark = [](int) {};
+#endif
   for (int k = 0; t < ntiles; ++k, t += gridDim.x) {
     const int c = t / tiles_per_c, r = t - c * tiles_per_c;
     const int by = r / ntx, bx = r - by * ntx;
@@ -292,8 +299,10 @@ k_conv_fft(const __grid_constant__ CUtensorMap tm_in, const float* __restrict__ 
       }
     }
   }
+#ifdef RLTV_PHASE_PROBE
   if (tid == 0)
     for (int i = 0; i < 6; ++i) atomicAdd(&g_fft_phase_cycles[i], (unsigned long long)ph[i]);
+#endif
   if (ADJ && cp.nranks > 1) band_step_max_tail(st, cp, seq, done_counter, reinterpret_cast<int*>(smem));
 }
 

@@ -168,7 +168,8 @@ int rltv_debug_download_err(rltv_ctx* ctx, float* err_out);
 /* TV(u, out, M, N, epsilon, order, norm, div) (pyx:137-239) of the estimate on the device; order, norm in {1,2};
  * out/div: packed HWC (M+MK-1, N+MK-1, 3), zero on the border ring; *ms = device time of the stencil kernel */
 int rltv_stage_tv(rltv_ctx* ctx, int32_t order, int32_t norm, float epsilon, float* out, float* div, float* ms);
-/* debug: cycles spent per phase of the row-FFT stencil kernel since the last call (8 counters), then reset */
+/* debug: cycles spent per phase of the row-FFT stencil kernel since the last call (8 counters), then reset;
+ * all zero unless the library was built with -DRLTV_PHASE_PROBE */
 int rltv_debug_phase_cycles(uint64_t* out8);
 /* test entry point of the shared-memory FFT engine used by the row-FFT stencils: nrows x 128 complex values
  * (interleaved re, im), forward (exp(-i..)) or unnormalised inverse */

@@ -1,4 +1,7 @@
-"""Per-phase cycle breakdown of the row-FFT stencil kernel on the headline workload (debug tool)."""
+"""Per-phase cycle breakdown of the row-FFT stencil kernel on the headline workload (debug tool).
+
+Needs a probe build:  RLTV_NVCC_EXTRA=-DRLTV_PHASE_PROBE python -c "import __graft_entry__ as g; g.build(force=True)"
+(the production build leaves the counters out: they cost the kernel register spills)."""
 import ctypes as C, sys
 sys.path.insert(0, ".")
 import numpy as np
