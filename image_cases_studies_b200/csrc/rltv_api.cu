@@ -155,8 +155,13 @@ void prof_collect(rltv_ctx* c) {
 }
 
 // ---- K-dispatch ------------------------------------------------------------------------------------
+// (-DRLTV_K_LIST="M(15)" restricts the instantiations: seconds instead of minutes for a kernel-development build)
+#ifdef RLTV_K_LIST
+#define RLTV_FOR_EACH_K(M) RLTV_K_LIST
+#else
 #define RLTV_FOR_EACH_K(M) \
   M(3) M(5) M(7) M(9) M(11) M(13) M(15) M(17) M(19) M(21) M(23) M(25) M(27) M(29) M(31)
+#endif
 
 // ---- TMA descriptors ---------------------------------------------------------------------------------
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -206,8 +211,8 @@ int make_maps_t(rltv_ctx* c) {
   if ((rc = make_tmap(&c->tm_err_gk, c->err + size_t(g.own0) * g.pitch, g, g.own1 - g.own0, G::TW, G::TH))) return rc;
   if constexpr (K >= 9) {
     using F = FftCfg<K>;
-    if ((rc = make_tmap(&c->tm_u_fft, c->u, g, g.Hu, FFT_N, F::IN_ROWS))) return rc;
-    if ((rc = make_tmap(&c->tm_err_fft, c->err, g, g.Hu, FFT_N, F::IN_ROWS))) return rc;
+    if ((rc = make_tmap(&c->tm_u_fft, c->u, g, g.Hu, F::INW, F::IN_ROWS))) return rc;
+    if ((rc = make_tmap(&c->tm_err_fft, c->err, g, g.Hu, F::INW, F::IN_ROWS))) return rc;
   }
   if constexpr (K >= 9) {
     using GF = GradkFftCfg<K>;

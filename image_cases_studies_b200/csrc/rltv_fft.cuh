@@ -9,6 +9,13 @@
 // (Cooley-Tukey with n = t + 8j, k = q + 16p.)  One shared-memory round trip per pass: 32 B of traffic per point.
 // The exchange pitch of 9 and a row pitch of FFT_PITCH = 152 complex (== 16 banks mod 32) make every LDS.64 /
 // STS.64 of a half-warp conflict-free.  Only __syncwarp() is needed inside: a row never leaves its 8 threads.
+//
+// Arithmetic: every complex value lives in one 64-bit register pair and every operation is a packed sm_100a
+// instruction (FADD2 / FMUL2 / FFMA2 through __fadd2_rn / __fmul2_rn / __ffma2_rn).  The hardware operand modifiers
+// do the rest for free: a half swap (.LO_HI), a per-half sign (.NP / .PN) and a scalar broadcast (.F32) -- so a complex
+// add is ONE instruction, a multiplication by +-i costs nothing (it folds into the consumer), and a complex
+// multiplication is TWO:   x * w = FFMA2(x, w.re, FMUL2((-x.im, x.re), w.im)).   Half the issue slots of the scalar
+// form for the same FMA-pipe work; the kernels around this engine are issue-bound, not pipe-bound.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -16,13 +23,27 @@ namespace rltv {
 
 constexpr int FFT_N = 128;
 constexpr int FFT_PITCH = 152;   // complex elements per row buffer (>= 9*16 = 144 exchange slots)
+// Pass-A twiddle table: tw[q][t'] = exp(-2 pi i t' q / 128), q = 0..15, t' = 0..31.  For a fixed q the 32 lanes of a
+// warp read 32 consecutive entries (conflict-free; the plain 128-entry table was read with stride q: up to 8-way
+// conflicts), and the index is a compile-time offset from a per-thread base.
+constexpr int FFT_TW_ENTRIES = 16 * 32;
+constexpr int FFT_TW_BYTES = FFT_TW_ENTRIES * 8;
 
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
-  return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+// a * w, two packed instructions
+__device__ __forceinline__ float2 cmulf(float2 a, float2 w) {
+  return __ffma2_rn(a, make_float2(w.x, w.x), __fmul2_rn(make_float2(-a.y, a.x), make_float2(w.y, w.y)));
 }
-// multiply by -i (forward) or +i (inverse)
+// acc + a * w (complex), two packed instructions
+__device__ __forceinline__ float2 cfma(float2 a, float2 w, float2 acc) {
+  return __ffma2_rn(make_float2(-a.y, a.x), make_float2(w.y, w.y), __ffma2_rn(a, make_float2(w.x, w.x), acc));
+}
+// acc + conj(e) * z, two packed instructions
+__device__ __forceinline__ float2 cfma_conj(float2 e, float2 z, float2 acc) {
+  return __ffma2_rn(make_float2(z.y, -z.x), make_float2(e.y, e.y), __ffma2_rn(z, make_float2(e.x, e.x), acc));
+}
+// multiply by -i (forward) or +i (inverse): folds into the consumer's operand modifiers
 template <bool INV>
 __device__ __forceinline__ float2 mul_mi(float2 a) { return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x); }
 
@@ -64,7 +85,10 @@ __device__ __forceinline__ void dft16(float2 (&x)[16]) {
 #pragma unroll
   for (int a = 1; a < 4; ++a)
 #pragma unroll
-    for (int c = 1; c < 4; ++c) x[a + 4 * c] = cmulf(x[a + 4 * c], w16<INV>(a * c));
+    for (int c = 1; c < 4; ++c) {
+      if (a * c == 4) x[a + 4 * c] = mul_mi<INV>(x[a + 4 * c]);                 // w16^4 = -+i: free
+      else x[a + 4 * c] = cmulf(x[a + 4 * c], w16<INV>(a * c));
+    }
 #pragma unroll
   for (int c = 0; c < 4; ++c) dft4<INV>(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);   // result d at x[4c + d]
   // now x[4c + d] = X[c + 4d]: transpose the 4x4 index
@@ -86,15 +110,9 @@ __device__ __forceinline__ void dft8(float2 (&x)[8]) {
   dft4<INV>(x[0], x[2], x[4], x[6]);   // Y[0][c] at x[2c]
   dft4<INV>(x[1], x[3], x[5], x[7]);   // Y[1][c] at x[2c+1]
   // w8^1 = (1 -+ i)/sqrt2, w8^2 = -+i, w8^3 = (-1 -+ i)/sqrt2
-  {
-    const float2 v = x[3];
-    x[3] = INV ? make_float2((v.x - v.y) * SQ, (v.x + v.y) * SQ) : make_float2((v.x + v.y) * SQ, (v.y - v.x) * SQ);
-  }
+  x[3] = cmulf(x[3], make_float2(SQ, INV ? SQ : -SQ));
   x[5] = mul_mi<INV>(x[5]);
-  {
-    const float2 v = x[7];
-    x[7] = INV ? make_float2((-v.x - v.y) * SQ, (v.x - v.y) * SQ) : make_float2((v.y - v.x) * SQ, (-v.x - v.y) * SQ);
-  }
+  x[7] = cmulf(x[7], make_float2(-SQ, INV ? SQ : -SQ));
   float2 y[8];
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
@@ -105,39 +123,35 @@ __device__ __forceinline__ void dft8(float2 (&x)[8]) {
   for (int k = 0; k < 8; ++k) x[k] = y[k];
 }
 
-// tw128[m] = exp(-2 pi i m / 128), m = 0..127, in shared memory (filled once per CTA by fft_fill_twiddles)
-__device__ __forceinline__ void fft_fill_twiddles(float2* tw128) {
-  for (int m = threadIdx.x; m < FFT_N; m += blockDim.x) {
+// tw[q * 32 + t'] = exp(-2 pi i t' q / 128) in shared memory (filled once per CTA)
+__device__ __forceinline__ void fft_fill_twiddles(float2* tw) {
+  for (int m = threadIdx.x; m < FFT_TW_ENTRIES; m += blockDim.x) {
+    const int q = m >> 5, tp = m & 31;
     float s, c;
-    sincospif(-2.0f * float(m) / float(FFT_N), &s, &c);
-    tw128[m] = make_float2(c, s);
+    sincospif(-2.0f * float((tp * q) & (FFT_N - 1)) / float(FFT_N), &s, &c);
+    tw[m] = make_float2(c, s);
   }
 }
 
-// Pass A + B of one row for the 8 threads (t = 0..7) that own it.  `load(n)` returns input element n.
+// Pass A + B of one row for the 8 threads (t = 0..7) that own it.  `load(j)` returns input element t + 8*((j + rot) & 15)
+// -- the caller does the addressing, so that a dense source can use compile-time offsets.
 // On return the row buffer `row` (FFT_PITCH complex) holds the spectrum / signal in natural order [0,128).
-// `rot` (0..15) rotates the order in which the 16 stride-8 samples are fetched (x'[j] = x[(j + rot) mod 16]); by the
-// shift theorem that only changes the pass-A twiddle index.  The four rows a warp handles use different `rot`, so
-// their loads from a dense 512-byte-pitch source (the TMA buffer) fall into different banks.
+// `rot` (0..3) rotates the order in which the 16 stride-8 samples are fetched (x'[j] = x[(j + rot) mod 16]); by the
+// shift theorem that only changes the pass-A twiddle index.  Callers whose four rows per warp would otherwise read
+// the same banks of a dense 512-byte-pitch source use different `rot` per row; everybody else passes 0.
 template <bool INV, typename Load>
-__device__ __forceinline__ void fft128_row(float2* __restrict__ row, const float2* __restrict__ tw128, int t, Load load,
-                                           unsigned mask = 0xffffffffu, int rot = 0) {
+__device__ __forceinline__ void fft128_core(float2* __restrict__ row, const float2* __restrict__ tw, int t, Load load,
+                                            unsigned mask, int rot) {
   float2 x[16];
-  const int base = t + 8 * rot;                  // rot <= 3: only j >= 13 can wrap around
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    int n = base + 8 * j;
-    if (j >= 13 && n >= FFT_N) n -= FFT_N;
-    x[j] = load(n);
-  }
+  for (int j = 0; j < 16; ++j) x[j] = load(j);
   dft16<INV>(x);                                 // X'[q] = X[q] * w16^(-rot q)   (forward; conjugate for inverse)
   __syncwarp(mask);                              // everyone's loads are done before anyone stores (in-place rows)
   row[t] = x[0];
-  int widx = 0;
+  const float2* twp = tw + (t + 8 * rot);        // w128^((t + 8 rot) q): w128^(t q) * w16^(+rot q) undoes the rotation
 #pragma unroll
   for (int q = 1; q < 16; ++q) {
-    widx = (widx + base) & (FFT_N - 1);          // (t + 8 rot) q mod 128: w128^(t q) * w16^(+rot q) undoes the rotation
-    float2 w = tw128[widx];
+    float2 w = twp[q * 32];
     if (INV) w.y = -w.y;
     row[9 * q + t] = cmulf(x[q], w);
   }
@@ -159,11 +173,19 @@ __device__ __forceinline__ void fft128_row(float2* __restrict__ row, const float
   }
 }
 
+// Generic form: `load(n)` returns input element n in [0, 128).
+template <bool INV, typename Load>
+__device__ __forceinline__ void fft128_row(float2* __restrict__ row, const float2* __restrict__ tw, int t, Load load,
+                                           unsigned mask = 0xffffffffu, int rot = 0) {
+  const int base = t + 8 * rot;
+  fft128_core<INV>(row, tw, t, [&](int j) { return load((base + 8 * j) & (FFT_N - 1)); }, mask, rot);
+}
+
 // Debug / test kernel: transforms `nrows` rows of 128 complex values (global, packed) one CTA per 16 rows.
 template <bool INV>
 __global__ void __launch_bounds__(128) k_fft128_debug(const float2* __restrict__ in, float2* __restrict__ out, int nrows) {
   __shared__ float2 buf[16 * FFT_PITCH];
-  __shared__ float2 tw[FFT_N];
+  __shared__ float2 tw[FFT_TW_ENTRIES];
   fft_fill_twiddles(tw);
   __syncthreads();
   const int r = threadIdx.x >> 3, t = threadIdx.x & 7;
@@ -171,7 +193,7 @@ __global__ void __launch_bounds__(128) k_fft128_debug(const float2* __restrict__
   if (row < nrows) {
     const unsigned mask = __activemask();
     const float2* src = in + size_t(row) * FFT_N;
-    fft128_row<INV>(buf + r * FFT_PITCH, tw, t, [&](int n) { return src[n]; }, mask);
+    fft128_row<INV>(buf + r * FFT_PITCH, tw, t, [&](int n) { return src[n]; }, mask, r & 3);
     __syncwarp(mask);
     for (int n = t; n < FFT_N; n += 8) out[size_t(row) * FFT_N + n] = buf[r * FFT_PITCH + n];
   }

@@ -40,12 +40,16 @@ struct FftCfg {
   static constexpr int CHUNK = HB / NCHUNK;        // output rows per MAC thread
   static constexpr int ER = THREADS / (TWO / 2);   // epilogue: 6 row slots x 56 column pairs
   static constexpr int NTASK = HB / ER;
-  static constexpr int IN_BYTES = IN_ROWS * FFT_N * 4;                        // TMA transaction size
+  // TMA box = INW x IN_ROWS floats.  INW = 136 (not 128): consecutive rows then start 8 banks apart, so the four rows
+  // a warp transforms read the dense TMA buffer conflict-free with compile-time offsets (no per-row fetch rotation).
+  static constexpr int INW = 136;
+  static constexpr int IN_BYTES = IN_ROWS * INW * 4;                          // TMA transaction size
+  static constexpr int IN_STRIDE = (IN_BYTES + 127) & ~127;
   static constexpr int ZB_BYTES = ZROWS * FFT_PITCH * 8;
   static constexpr int WS_BYTES = K * FFT_N * 8;                              // tap spectra of the current channel
   static_assert(NCHUNK * CHUNK == HB && ER * NTASK == HB, "MAC chunks / epilogue row slots cover the packed rows");
-  static_assert(IN_BYTES % 128 == 0 && ZB_BYTES % 128 == 0 && WS_BYTES % 128 == 0, "TMA destinations: 128-byte aligned");
-  static constexpr int SMEM_BYTES = IN_BYTES + ZB_BYTES + WS_BYTES + FFT_N * 8 + 64 + 128;
+  static_assert(ZB_BYTES % 128 == 0 && WS_BYTES % 128 == 0, "128-byte aligned sections");
+  static constexpr int SMEM_BYTES = IN_STRIDE + ZB_BYTES + WS_BYTES + FFT_TW_BYTES + 64 + 128;
   static_assert(P4 + TWO - 1 + P <= FFT_N - 1, "segment too short for this K");
   static_assert(CTAS_PER_SM * SMEM_BYTES <= 227 * 1024, "shared memory");
 };
@@ -84,10 +88,10 @@ k_conv_fft(const __grid_constant__ CUtensorMap tm_in, const float* __restrict__ 
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
   const float* inR = reinterpret_cast<const float*>(smem);                       // real rows, TMA destination
-  float2* ZB = reinterpret_cast<float2*>(smem + C::IN_BYTES);                    // packed spectra, then outputs
-  float2* WS = reinterpret_cast<float2*>(smem + C::IN_BYTES + C::ZB_BYTES);      // tap spectra [K][128]
-  float2* tw = reinterpret_cast<float2*>(smem + C::IN_BYTES + C::ZB_BYTES + C::WS_BYTES);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(tw) + FFT_N * 8);
+  float2* ZB = reinterpret_cast<float2*>(smem + C::IN_STRIDE);                   // packed spectra, then outputs
+  float2* WS = reinterpret_cast<float2*>(smem + C::IN_STRIDE + C::ZB_BYTES);     // tap spectra [K][128]
+  float2* tw = reinterpret_cast<float2*>(smem + C::IN_STRIDE + C::ZB_BYTES + C::WS_BYTES);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(tw) + FFT_TW_BYTES);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tiles_per_c = ntx * nty, ntiles = 3 * tiles_per_c;
 
@@ -143,9 +147,8 @@ k_conv_fft(const __grid_constant__ CUtensorMap tm_in, const float* __restrict__ 
     for (int task = tid; task < C::ZROWS * 8; task += C::THREADS) {
       const unsigned mask = __activemask();
       const int zr = task >> 3, tt = task & 7;
-      const float* ra = inR + zr * FFT_N;
-      const float* rb = inR + (zr + C::HB) * FFT_N;
-      fft128_row<false>(ZB + zr * FFT_PITCH, tw, tt, [&](int n) { return make_float2(ra[n], rb[n]); }, mask, zr & 3);
+      const float* ra = inR + zr * C::INW + tt;
+      fft128_core<false>(ZB + zr * FFT_PITCH, tw, tt, [&](int j) { return make_float2(ra[8 * j], ra[C::HB * C::INW + 8 * j]); }, mask, 0);
     }
     __syncthreads();
     mark(1);
@@ -166,12 +169,7 @@ k_conv_fft(const __grid_constant__ CUtensorMap tm_in, const float* __restrict__ 
       for (int ky = 0; ky < K; ++ky) {
         const float2 w = WS[ky * FFT_N + bin];
 #pragma unroll
-        for (int y = 0; y < C::CHUNK; ++y) {
-          acc[y].x = fmaf(w.x, z[y + ky].x, acc[y].x);
-          acc[y].x = fmaf(-w.y, z[y + ky].y, acc[y].x);
-          acc[y].y = fmaf(w.x, z[y + ky].y, acc[y].y);
-          acc[y].y = fmaf(w.y, z[y + ky].x, acc[y].y);
-        }
+        for (int y = 0; y < C::CHUNK; ++y) acc[y] = cfma(z[y + ky], w, acc[y]);
       }
       __syncthreads();                      // every chunk has read its window (chunks overlap by K-1 rows)
 #pragma unroll
@@ -340,7 +338,7 @@ struct GradkFftCfg {
   static constexpr int E_BYTES = TROWS * FFT_N * 4;
   static constexpr int ZU_BYTES = ZU_ROWS * FFT_PITCH * 8;
   static constexpr int ZE_BYTES = HB * FFT_PITCH * 8;
-  static constexpr int SMEM_BYTES = U_BYTES + E_BYTES + ZU_BYTES + ZE_BYTES + FFT_N * 8 + 64 + 128;
+  static constexpr int SMEM_BYTES = U_BYTES + E_BYTES + ZU_BYTES + ZE_BYTES + FFT_TW_BYTES + 64 + 128;
   // fused variant (residual computed in the kernel): + the forward tap spectra of the current channel
   static constexpr int WS_BYTES = K * FFT_N * 8;
   static constexpr int SMEM_BYTES_FUSED = SMEM_BYTES + WS_BYTES;
@@ -375,7 +373,7 @@ k_gradk_fft(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
   float2* ZU = reinterpret_cast<float2*>(smem + C::U_BYTES + C::E_BYTES);
   float2* ZE = reinterpret_cast<float2*>(smem + C::U_BYTES + C::E_BYTES + C::ZU_BYTES);
   float2* tw = reinterpret_cast<float2*>(smem + C::U_BYTES + C::E_BYTES + C::ZU_BYTES + C::ZE_BYTES);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(tw) + FFT_N * 8);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(tw) + FFT_TW_BYTES);
   float2* WS = reinterpret_cast<float2*>(smem + C::SMEM_BYTES - 128);   // FUSED only: forward tap spectra [K][128]
   const int tid = threadIdx.x;
   const int tiles_per_c = ntx * nty;
@@ -482,12 +480,7 @@ k_gradk_fft(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
           for (int ky = 0; ky < K; ++ky) {
             const float2 w = WS[ky * FFT_N + bin];
 #pragma unroll
-            for (int y = 0; y < HC; ++y) {
-              o[y].x = fmaf(w.x, z[y + ky].x, o[y].x);
-              o[y].x = fmaf(-w.y, z[y + ky].y, o[y].x);
-              o[y].y = fmaf(w.x, z[y + ky].y, o[y].y);
-              o[y].y = fmaf(w.y, z[y + ky].x, o[y].y);
-            }
+            for (int y = 0; y < HC; ++y) o[y] = cfma(z[y + ky], w, o[y]);
           }
 #pragma unroll
           for (int y = 0; y < HC; ++y) ZE[(y0 + y) * FFT_PITCH + bin] = o[y];
@@ -548,11 +541,7 @@ k_gradk_fft(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
         const float2 e = ze0[y * FFT_PITCH];
 #pragma unroll
         for (int d = 0; d < K; ++d) {
-          const float2 z = win[(y + d) % K];
-          acc[d].x = fmaf(e.x, z.x, acc[d].x);
-          acc[d].x = fmaf(e.y, z.y, acc[d].x);
-          acc[d].y = fmaf(e.x, z.y, acc[d].y);
-          acc[d].y = fmaf(-e.y, z.x, acc[d].y);
+          acc[d] = cfma_conj(e, win[(y + d) % K], acc[d]);
         }
       }
     }
