@@ -54,7 +54,10 @@ def main(rep, json_out=None, workload=None):
 
     if json_out:
         import json
-        json.dump({"workload": workload, "source": rep.split("/")[-1],
+        import pathlib
+        sys.path.insert(0, str(pathlib.Path(__file__).resolve().parents[1]))
+        import bench                                   # the stamp bench.py checks before quoting these numbers
+        json.dump({"workload": workload, "source": rep.split("/")[-1], "csrc_sha16": bench.csrc_hash(),
                    "what": "dram__bytes_read.sum + dram__bytes_write.sum per launch (mean over the captured launches), ncu --set full",
                    "per_launch_dram_bytes": {f: sum(v) / len(v) for f, v in traffic.items()},
                    "launches_captured": {f: len(v) for f, v in traffic.items()}}, open(json_out, "w"), indent=1)
