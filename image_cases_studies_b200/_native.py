@@ -77,6 +77,7 @@ SYMBOLS = [
     ("rltv_poll_wait", C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]),
     ("rltv_stage_residual", C.c_int, [C.c_void_p, C.c_void_p]),
     ("rltv_stage_adjoint", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("rltv_stage_chain", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     ("rltv_stage_gradk", C.c_int, [C.c_void_p, C.c_void_p]),
     ("rltv_debug_download_err", C.c_int, [C.c_void_p, C.c_void_p]),
     ("rltv_stage_tv", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]),

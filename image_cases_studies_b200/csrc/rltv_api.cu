@@ -23,6 +23,7 @@
 
 #include "../../include/rltv_b200.h"
 #include "rltv_band.cuh"
+#include "rltv_chain_fft.cuh"
 #include "rltv_common.cuh"
 #include "rltv_elementwise.cuh"
 #include "rltv_fft.cuh"
@@ -80,6 +81,17 @@ struct rltv_ctx {
   CUtensorMap tm_img_gkfft;     // image rows of the owned rows, same boxes as tm_err_gkfft (fused residual)
   float2* gkf_part = nullptr;   // k_gradk_fft: per-CTA frequency-domain sums
   float2* wspec = nullptr;      // tap spectra [2][3][K][128]
+  // spectral chain kernel (11 <= K <= 17): forward blur + residual + adjoint in one pass (rltv_chain_fft.cuh)
+  bool use_chain = false;
+  CUtensorMap tm_u_chain{};
+  ChainPiece* chain_pieces = nullptr;   // device
+  int* chain_first = nullptr;           // device: [num_sms + 1] first piece of every CTA
+  int chain_npieces = 0;
+  float2* chain_ipk = nullptr;          // packed image spectra, one row of 128 bins per packed residual row of every piece
+  size_t chain_ipk_rows = 0;
+  bool chain_ipk_valid = false;
+  int inner_count = 0;                  // inner steps enqueued since rltv_begin (statistics slot = parity)
+  int inner_in_outer = 0;               // 0 right after ut = u
   bool use_fft = false;         // forward blur / adjoint through k_conv_fft
   bool use_fft_gradk = false;   // PSF gradient through k_gradk_fft
   bool fuse_residual = false;   // ... which also computes the residual of pyx:557-565 itself (no forward-blur launch)
@@ -248,6 +260,38 @@ int launch_conv_fft_t(rltv_ctx* c, float lambd) {
   }
 }
 
+// forward blur + residual on local rows [y0, y1) only (chain path, non-blind: the whiteness window, pyx:623-638)
+template <int K>
+int launch_conv_fwd_rows_t(rltv_ctx* c, int y0, int y1) {
+  if constexpr (K >= 9) {
+    using C = FftCfg<K>;
+    constexpr int SMEM = C::SMEM_BYTES;
+    CU(cudaFuncSetAttribute(k_conv_fft<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    const int ntx = (c->g.Wu + C::TWO - 1) / C::TWO, nty = (y1 - y0 + C::TROWS - 1) / C::TROWS;
+    int grid = C::CTAS_PER_SM * c->num_sms;
+    if (grid > 3 * ntx * nty) grid = 3 * ntx * nty;
+    ProfScope p(c, F_STATS);
+    k_conv_fft<K, false><<<grid, C::THREADS, SMEM, c->stream>>>(c->tm_u_fft, c->img, c->img, c->g, c->st, c->wspec, 0.f, c->err,
+                                                              ntx, nty, y0, y1, c->peers, 0, c->counters + 1);
+    return RLTV_OK;
+  } else {
+    return fail(RLTV_ERR_ARG, "row-FFT stencils exist for MK >= 9");
+  }
+}
+
+int launch_conv_fwd_window(rltv_ctx* c) {
+  int y0 = c->wg.top + c->g.P - c->g.row0, y1 = y0 + c->wg.h;
+  if (y0 < 0) y0 = 0;
+  if (y1 > c->g.Hu) y1 = c->g.Hu;
+  switch (c->g.K) {
+    case 11: return launch_conv_fwd_rows_t<11>(c, y0, y1);
+    case 13: return launch_conv_fwd_rows_t<13>(c, y0, y1);
+    case 15: return launch_conv_fwd_rows_t<15>(c, y0, y1);
+    case 17: return launch_conv_fwd_rows_t<17>(c, y0, y1);
+  }
+  return fail(RLTV_ERR_ARG, "unsupported MK");
+}
+
 int launch_psf_spectrum(rltv_ctx* c) {
   if (!c->use_fft) return RLTV_OK;
   ProfScope p(c, F_PSF);
@@ -360,10 +404,121 @@ int launch_gradk(rltv_ctx* c) {
 int launch_update(rltv_ctx* c) {
   dim3 grid((c->g.pitch / 4 + 255) / 256, c->g.own1 - c->g.own0, 3);
   ProfScope p(c, F_UPDATE);
+  // chain path: this step's statistics are in slot (inner_count & 1); the update resets the other slot for the next step
+  const int slot = c->use_chain ? (c->inner_count & 1) : 0;
+  const int reset_slot = c->use_chain ? (slot ^ 1) : -1;
   k_update<<<grid, 256, 0, c->stream>>>(c->g, c->st, c->u, c->ut, c->gbuf, c->img, c->params.step_factor,
-                                        c->params.lambd, c->params.blind);
+                                        c->params.lambd, c->params.blind, slot, reset_slot);
   return RLTV_OK;
 }
+
+// ---- spectral chain kernel: work partition, image spectra, launch -------------------------------------------
+template <int K>
+int chain_setup_t(rltv_ctx* c) {
+  if constexpr (K >= 9 && K <= 17) {
+    using C = ChainCfg<K>;
+    const Geom& g = c->g;
+    const int nseg = chain_nseg(g.Wu, C::V), nstrips = 3 * nseg, G = c->num_sms;
+    const int y0 = g.own0, y1 = g.own1, R = y1 - y0;
+    auto xfix = [&](int s) { const int X0 = C::V * s - (K - 1); return !(X0 >= 0 && X0 + FFT_N <= g.Wu); };
+    // balanced split of the weighted row sequence (strip-major) into one contiguous range per CTA; a border strip
+    // (masking path every step) counts 1.7x
+    std::vector<double> wsum(nstrips + 1, 0.0);
+    for (int i = 0; i < nstrips; ++i) wsum[i + 1] = wsum[i] + (xfix(i % nseg) ? 1.7 : 1.0) * R;
+    const double total = wsum[nstrips];
+    auto pos_of = [&](double w, int& strip, int& row) {      // inverse of the cumulative weight
+      strip = 0;
+      while (strip + 1 < nstrips && wsum[strip + 1] <= w) ++strip;
+      const double per = (wsum[strip + 1] - wsum[strip]) / R;
+      row = int((w - wsum[strip]) / per + 0.5);
+      if (row > R) row = R;
+      if (row < 0) row = 0;
+    };
+    std::vector<ChainPiece> pieces;
+    std::vector<int> first(G + 1, 0);
+    size_t ipk_rows = 0;
+    int ps = 0, pr = 0;                                       // current position (strip, row)
+    for (int b = 0; b < G; ++b) {
+      first[b] = int(pieces.size());
+      int es, er;
+      if (b == G - 1) { es = nstrips - 1; er = R; } else pos_of(total * (b + 1) / G, es, er);
+      while (ps < es || (ps == es && pr < er)) {
+        const int rend = (ps < es) ? R : er;
+        if (rend > pr) {
+          const int n = rend - pr;
+          ChainPiece pc;
+          pc.c = ps / nseg; pc.s = ps % nseg;
+          pc.ya = y0 + pr; pc.L = (n + 1) / 2; pc.Lb = n - pc.L;
+          pc.nsteps = (pc.L + 4 * C::P + C::S - 1) / C::S;
+          pc.ipk_row0 = int(ipk_rows);
+          pc.xfix = xfix(pc.s) ? 1 : 0;
+          ipk_rows += size_t(pc.nsteps) * C::S;
+          pieces.push_back(pc);
+        }
+        if (ps < es) { ++ps; pr = 0; } else pr = rend;
+      }
+    }
+    first[G] = int(pieces.size());
+    if (ipk_rows * FFT_N >= (size_t(1) << 31)) return fail(RLTV_ERR_ARG, "frame too large for the chain kernel's piece table");
+    cudaFree(c->chain_pieces); cudaFree(c->chain_first); cudaFree(c->chain_ipk);
+    c->chain_pieces = nullptr; c->chain_first = nullptr; c->chain_ipk = nullptr;
+    c->chain_npieces = int(pieces.size());
+    c->chain_ipk_rows = ipk_rows;
+    CU(cudaMalloc(&c->chain_pieces, pieces.size() * sizeof(ChainPiece)));
+    CU(cudaMalloc(&c->chain_first, (G + 1) * sizeof(int)));
+    CU(cudaMalloc(&c->chain_ipk, ipk_rows * FFT_N * sizeof(float2)));
+    CU(cudaMemcpyAsync(c->chain_pieces, pieces.data(), pieces.size() * sizeof(ChainPiece), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->chain_first, first.data(), (G + 1) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    int rc;
+    if ((rc = make_tmap(&c->tm_u_chain, c->u, g, g.Hu, C::INW, C::S))) return rc;
+    CU(cudaFuncSetAttribute(k_chain_fft<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    c->chain_ipk_valid = false;
+    return RLTV_OK;
+  } else {
+    return fail(RLTV_ERR_ARG, "the chain kernel exists for 9 <= MK <= 17");
+  }
+}
+
+template <int K>
+int chain_image_spectra_t(rltv_ctx* c) {
+  if constexpr (K >= 9 && K <= 17) {
+    k_chain_image_spectra<K><<<dim3(8, c->chain_npieces < 2048 ? c->chain_npieces : 2048), 256, 0, c->stream>>>(
+        c->g, c->img, c->chain_pieces, c->chain_npieces, c->chain_ipk);
+    c->launches++;
+    c->chain_ipk_valid = true;
+    return RLTV_OK;
+  } else {
+    return fail(RLTV_ERR_ARG, "the chain kernel exists for 9 <= MK <= 17");
+  }
+}
+
+template <int K>
+int launch_chain_t(rltv_ctx* c, float lambd) {
+  if constexpr (K >= 9 && K <= 17) {
+    using C = ChainCfg<K>;
+    if (c->peers.nranks > 1) c->max_seq += 1;
+    ProfScope p(c, F_CONV_ADJ);
+    k_chain_fft<K><<<c->num_sms, C::THREADS, C::SMEM_BYTES, c->stream>>>(
+        c->tm_u_chain, c->g, c->st, c->wspec, c->chain_ipk, c->chain_pieces, c->chain_first, c->u, c->ut, lambd, c->gbuf,
+        c->inner_count & 1, c->inner_in_outer == 0 ? 1 : 0, c->peers, c->max_seq, c->counters + 1);
+    return RLTV_OK;
+  } else {
+    return fail(RLTV_ERR_ARG, "the chain kernel exists for 9 <= MK <= 17");
+  }
+}
+
+#define RLTV_CHAIN_DISPATCH(FN, ...)                                   \
+  switch (c->g.K) {                                                    \
+    case 11: return FN<11>(__VA_ARGS__);                               \
+    case 13: return FN<13>(__VA_ARGS__);                               \
+    case 15: return FN<15>(__VA_ARGS__);                               \
+    case 17: return FN<17>(__VA_ARGS__);                               \
+  }                                                                    \
+  return fail(RLTV_ERR_ARG, "the chain kernel exists for MK = 11..17");
+int chain_setup(rltv_ctx* c) { RLTV_CHAIN_DISPATCH(chain_setup_t, c) }
+int chain_image_spectra(rltv_ctx* c) { RLTV_CHAIN_DISPATCH(chain_image_spectra_t, c) }
+int launch_chain(rltv_ctx* c, float lambd) { RLTV_CHAIN_DISPATCH(launch_chain_t, c, lambd) }
 
 int launch_psf_update(rltv_ctx* c) {
   const int K = c->g.K;
@@ -487,14 +642,27 @@ int enqueue_phase(rltv_ctx* c, int phase) {
     case RLTV_PH_OUTER_BEGIN: {
       ProfScope p(c, F_COPY);                                      // ut[:] = u.copy(), pyx:462
       CU(cudaMemcpyAsync(c->ut, c->u, 3 * c->g.plane * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+      c->inner_in_outer = 0;
       return RLTV_OK;
     }
     case RLTV_PH_GRAD:
+      if (c->use_chain) {
+        if (!c->chain_ipk_valid && (rc = chain_image_spectra(c)) != RLTV_OK) return rc;
+        // the whiteness statistic reads the residual of the last inner step (pyx:623-638): in blind mode the PSF-gradient
+        // kernel leaves it behind, otherwise compute it on the window rows only.  Launched BEFORE the chain kernel: like
+        // every forward launch it resets statistics slot 0, which at this point is either already reset or unused.
+        if (!c->params.blind && c->white_owner && c->inner_in_outer == RLTV_INNER_ITER - 1)
+          if ((rc = launch_conv_fwd_window(c)) != RLTV_OK) return rc;
+        if ((rc = launch_chain(c, c->params.lambd)) != RLTV_OK) return rc;    // pyx:477-491, :519, :524 in one pass
+        return RLTV_OK;
+      }
       if ((rc = launch_conv_fwd(c)) != RLTV_OK) return rc;        // pyx:477-488
       if ((rc = launch_conv_adj(c, c->params.lambd)) != RLTV_OK) return rc;   // pyx:490-491, :519, :524
       return RLTV_OK;
     case RLTV_PH_UPDATE:
       if ((rc = launch_update(c)) != RLTV_OK) return rc;          // pyx:527-531, :499-502, :552
+      c->inner_count += 1;
+      c->inner_in_outer += 1;
       return launch_halo_push(c);
     case RLTV_PH_PSF_GRAD:
       if (!c->fuse_residual)
@@ -670,9 +838,16 @@ int rltv_create_band(rltv_ctx** out, int32_t device, int32_t M, int32_t N, int32
     c->use_fft_gradk = c->use_fft;
     c->fuse_residual = c->use_fft_gradk && MK <= 17;             // GradkFftCfg<K>::CAN_FUSE
     if (const char* e = getenv("RLTV_FUSE")) c->fuse_residual = c->fuse_residual && atoi(e) != 0;
+    // spectral chain kernel: default for the sizes it exists for; RLTV_CHAIN=0 keeps the two-kernel gradient path
+    c->use_chain = c->use_fft && MK >= 11 && MK <= 17;
+    if (const char* e = getenv("RLTV_CHAIN")) c->use_chain = c->use_chain && atoi(e) != 0;
   }
   {
     int rc = make_maps(c);
+    if (rc) { std::string keep = g_err; rltv_destroy(c); g_err = keep; return rc; }
+  }
+  if (c->use_chain) {
+    int rc = chain_setup(c);
     if (rc) { std::string keep = g_err; rltv_destroy(c); g_err = keep; return rc; }
   }
   CU(cudaStreamSynchronize(c->stream));
@@ -695,6 +870,7 @@ int rltv_destroy(rltv_ctx* c) {
   double* d[] = {c->gk_sum, c->wa, c->wb, c->rowacc, c->rowsum};
   for (auto p : d) cudaFree(p);
   cudaFree(c->Z); cudaFree(c->tw); cudaFree(c->st); cudaFree(c->counters); cudaFree(c->wspec); cudaFree(c->gkf_part);
+  cudaFree(c->chain_pieces); cudaFree(c->chain_first); cudaFree(c->chain_ipk);
   if (c->h_st) cudaFreeHost(c->h_st);
   if (c->h_poll) cudaFreeHost(c->h_poll);
   for (auto& e : c->poll_ev) if (e) cudaEventDestroy(e);
@@ -721,6 +897,7 @@ int rltv_upload_band(rltv_ctx* c, const float* image, size_t image_rs, int32_t i
     CU(cudaMemcpy2DAsync(c->staging, size_t(g.N) * 12, image, image_rs, size_t(g.N) * 12, n_image_rows, cudaMemcpyHostToDevice, c->stream));
     k_hwc_to_planar<<<dim3(hwc_grid(g.N), n_image_rows), 256, 0, c->stream>>>(c->staging, size_t(g.N) * 3, n_image_rows, g.N, c->img, g, dst, g.P);
     c->launches++;
+    c->chain_ipk_valid = false;                    // the chain kernel's packed image spectra follow the image
   }
   if (u) {
     if (u_rs < size_t(g.Wu) * 12) return fail(RLTV_ERR_ARG, "u row stride smaller than a packed row");
@@ -794,6 +971,9 @@ int rltv_begin(rltv_ctx* c, const rltv_params_t* p) {
   rc = setup_whiteness(c, p->top, p->bottom, p->left, p->right);
   if (rc) return rc;
   CU(cudaMemsetAsync(c->st, 0, sizeof(State), c->stream));
+  k_state_init<<<1, 32, 0, c->stream>>>(c->st);
+  c->inner_count = 0;
+  c->inner_in_outer = 0;
   c->outer_enqueued = 0;
   c->outer_since_begin = 0;
   c->launches = 0;
@@ -912,6 +1092,7 @@ int rltv_set_rank(rltv_ctx* c, int32_t rank, int32_t world, int32_t fused) {
   c->peers.rank = c->fused_comm ? rank : 0;
   c->peers.nranks = c->fused_comm ? world : 1;
   if (!c->fused_comm) c->rank = 0;   // kernels index peers.peer[c->rank]; the NCCL baseline never exchanges in-kernel
+  if (!c->fused_comm && world > 1) c->use_chain = false;   // the host all-reduces statistics slot 0 between two kernels
   return RLTV_OK;
 }
 
@@ -972,7 +1153,7 @@ void* rltv_device_ptr(rltv_ctx* c, const char* name, size_t* nbytes) {
   if (!c || !name) return nullptr;
   size_t n = 0;
   void* p = nullptr;
-  if (!std::strcmp(name, "step_max")) { p = c->st->max_u; n = 6 * sizeof(int); }
+  if (!std::strcmp(name, "step_max")) { p = c->st->smax[0]; n = 6 * sizeof(int); }
   else if (!std::strcmp(name, "gk_sum")) { p = c->gk_sum; n = size_t(3) * c->g.K * c->g.K * sizeof(double); }
   else if (!std::strcmp(name, "stop")) { p = &c->st->stop; n = sizeof(int); }
   if (nbytes) *nbytes = n;
@@ -1011,6 +1192,36 @@ int rltv_stage_adjoint(rltv_ctx* c, float* g_out) {
   }
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaGetLastError());
+  return RLTV_OK;
+}
+
+int rltv_stage_chain(rltv_ctx* c, float* g_out, float* max6) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  if (!c->uploaded) return fail(RLTV_ERR_STATE, "upload first");
+  if (c->banded) return fail(RLTV_ERR_STATE, "stage entry points need a whole-frame context");
+  if (!c->use_chain) return fail(RLTV_ERR_STATE, "this context does not use the chain kernel (MK outside 11..17 or RLTV_CHAIN=0)");
+  const Geom& g = c->g;
+  CU(cudaMemsetAsync(c->st, 0, sizeof(State), c->stream));
+  k_state_init<<<1, 32, 0, c->stream>>>(c->st);
+  c->inner_count = 0;
+  c->inner_in_outer = 0;                           // ut = u
+  if (!c->chain_ipk_valid && (rc = chain_image_spectra(c)) != RLTV_OK) return rc;
+  if ((rc = launch_chain(c, 1.0f)) != RLTV_OK) return rc;
+  if (g_out) {
+    k_planar_to_hwc<<<dim3(8, g.Hu), 256, 0, c->stream>>>(c->gbuf, g, 0, 0, g.Hu, g.Wu, c->staging, size_t(g.Wu) * 3);
+    CU(cudaMemcpyAsync(g_out, c->staging, size_t(g.Hu) * g.Wu * 12, cudaMemcpyDeviceToHost, c->stream));
+  }
+  int h[6];
+  CU(cudaMemcpyAsync(h, c->st->smax[0], sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  if (max6)
+    for (int i = 0; i < 6; ++i) {
+      const int o = h[i];
+      const int b = o >= 0 ? o : (o ^ 0x7fffffff);
+      std::memcpy(&max6[i], &b, 4);
+    }
   return RLTV_OK;
 }
 

@@ -96,13 +96,13 @@ k_halo_push(Geom g, const State* __restrict__ st, const float* __restrict__ u, H
 }
 
 // Called by ONE thread of the last CTA of the adjoint kernel: publish this band's step scalars to every band.
-__device__ __forceinline__ void publish_step_max(State* st, const CommPeers& cp, int seq) {
+__device__ __forceinline__ void publish_step_max(State* st, int slot, const CommPeers& cp, int seq) {
   const int par = seq & 1;
   int v[6];
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
-    v[i] = atomicMax(&st->max_u[i], ORD_LOWEST);      // atomic read of the final value
-    v[3 + i] = atomicMax(&st->max_G[i], ORD_LOWEST);
+    v[i] = atomicMax(&st->smax[slot][i], ORD_LOWEST);      // atomic read of the final value
+    v[3 + i] = atomicMax(&st->smax[slot][3 + i], ORD_LOWEST);
   }
   for (int r = 0; r < cp.nranks; ++r) {
     volatile int* dst = cp.peer[r]->max_val[par][cp.rank];
@@ -117,7 +117,7 @@ __device__ __forceinline__ void publish_step_max(State* st, const CommPeers& cp,
 // Warp 0 of the last CTA of the adjoint kernel, right after publish_step_max: wait for every band's scalars of step
 // `seq` and reduce them with max into the local State (pyx:524).  No band's publication depends on this wait, so
 // there is no cycle; the update kernel that follows in stream order sees the global maxima.
-__device__ __forceinline__ void gather_step_max(State* st, Comm* mine, int nranks, int seq, int lane) {
+__device__ __forceinline__ void gather_step_max(State* st, int slot, Comm* mine, int nranks, int seq, int lane) {
   const int par = seq & 1;
   if (lane < nranks) spin_until(&mine->max_flag[par][lane], seq);
   __syncwarp();
@@ -125,13 +125,13 @@ __device__ __forceinline__ void gather_step_max(State* st, Comm* mine, int nrank
   if (lane < 6) {
     int m = ORD_LOWEST;
     for (int r = 0; r < nranks; ++r) m = max(m, *reinterpret_cast<volatile int*>(&mine->max_val[par][r][lane]));
-    if (lane < 3) st->max_u[lane] = m; else st->max_G[lane - 3] = m;
+    st->smax[slot][lane] = m;
   }
 }
 
 // Tail of the adjoint kernels with row bands: the last CTA to finish publishes this band's step scalars to every band
 // (peer stores) and gathers everybody's.  `slot` is one free word of shared memory; call with all threads.
-__device__ __forceinline__ void band_step_max_tail(State* st, const CommPeers& cp, int seq, unsigned* done_counter, int* slot) {
+__device__ __forceinline__ void band_step_max_tail_slot(State* st, int sslot, const CommPeers& cp, int seq, unsigned* done_counter, int* slot) {
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -139,12 +139,15 @@ __device__ __forceinline__ void band_step_max_tail(State* st, const CommPeers& c
     if (last) {
       *done_counter = 0u;
       __threadfence();
-      publish_step_max(st, cp, seq);
+      publish_step_max(st, sslot, cp, seq);
     }
     *slot = last;
   }
   __syncthreads();
-  if (*slot && threadIdx.x < 32) gather_step_max(st, cp.peer[cp.rank], cp.nranks, seq, threadIdx.x);
+  if (*slot && threadIdx.x < 32) gather_step_max(st, sslot, cp.peer[cp.rank], cp.nranks, seq, threadIdx.x);
+}
+__device__ __forceinline__ void band_step_max_tail(State* st, const CommPeers& cp, int seq, unsigned* done_counter, int* slot) {
+  band_step_max_tail_slot(st, 0, cp, seq, done_counter, slot);
 }
 
 // Non-owning bands: wait for the stop decision of outer iteration `seq` from the band that holds the window.

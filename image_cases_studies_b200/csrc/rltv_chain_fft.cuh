@@ -123,24 +123,23 @@ __device__ __forceinline__ void named_bar_arrive(int id, int count) {
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
-// MAC over one 8-row block:  acc[y] = sum_ky w[ky] * win[y + ky],  win[x] = x < T2 ? tail[x] : cur[x - T2]
-// (x0 = first window row of the block).  CONJ: this thread's bin is > 64 and reads the tap spectrum of bin 128 - k.
-template <int K, int X0, bool CONJ, int TPITCH, int CPITCH>
-__device__ __forceinline__ void chain_mac_block(const float2* __restrict__ tail, const float2* __restrict__ cur,
-                                                const float2* __restrict__ w, float2 (&acc)[8]) {
+// MAC over one 8-row block with a ROLLING register window:  acc[y] = sum_ky w[ky] * z[y + ky], where z[0 .. 2P) are the
+// last 2P window rows of the previous block (or the rows carried over from the previous step) and z[2P .. 2P + 8) the
+// block's own 8 rows, loaded here.  On return the window has moved down by 8 rows.  The loop over the three blocks of
+// a step is NOT unrolled: a MAC warp runs alone on its scheduler, and straight-line code of a whole step (~30 KB) made
+// the role instruction-fetch bound (ncu: 'no instruction' was its top stall); one block body fits the L0 cache.
+template <int K, int CPITCH>
+__device__ __forceinline__ void chain_mac_block(float2 (&z)[8 + K - 1], const float2* __restrict__ cur,
+                                                const float2* __restrict__ w, float sgn, float2 (&acc)[8]) {
   using C = ChainCfg<K>;
-  float2 z[8 + K - 1];
 #pragma unroll
-  for (int m = 0; m < 8 + K - 1; ++m) {
-    const int x = X0 + m;
-    z[m] = (x < C::T2) ? tail[x * TPITCH] : cur[(x - C::T2) * CPITCH];
-  }
+  for (int m = 0; m < 8; ++m) z[C::T2 + m] = cur[m * CPITCH];
 #pragma unroll
   for (int y = 0; y < 8; ++y) acc[y] = make_float2(0.f, 0.f);
 #pragma unroll
   for (int ky = 0; ky < K; ++ky) {
     float2 wv = w[ky * C::WP];
-    if (CONJ) wv.y = -wv.y;
+    wv.y *= sgn;                       // bins above 64 read the spectrum of bin 128 - k: conjugate (real taps)
 #pragma unroll
     for (int y = 0; y < 8; ++y) acc[y] = cfma(z[y + ky], wv, acc[y]);
   }
@@ -205,13 +204,17 @@ k_chain_fft(const __grid_constant__ CUtensorMap tm_u, Geom g, State* __restrict_
   // a step needs the slow (masking) path if its residual rows touch rows outside the image or the segment is a border one
   auto needs_fix = [&](const ChainPiece& pc, int j) {
     const int ea = pc.ya + j * C::S - 3 * C::P, eb = ea + pc.L;
-    const bool rowfix = (ea < imgLo && ea + C::S > imgLo - 0 && ea + C::S > 0) || (ea + C::S > imgHi) || (eb < imgLo) || (eb + C::S > imgHi);
+    const bool rowfix = (ea < imgLo) || (ea + C::S > imgHi) || (eb < imgLo) || (eb + C::S > imgHi);
     return pc.xfix || rowfix;
   };
 
   ChainCursor cf{p0, 0}, cm{p0, 0}, ci{p0, 0};          // forward FFT / MAC / inverse FFT cursors
   if (tid == 0) issue(pieces[p0], 0);
   float mu = -INFINITY, mG = 0.f;                       // inverse-FFT role: statistics of the current piece's channel
+  constexpr int NQ = (C::V / 4 + 7) / 8;                // float4 columns per thread of a row's 8-thread group
+  float4 da[NQ], db[NQ];                                // inverse-FFT role: (u - ut)/2 under its next g row pair
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) da[q] = db[q] = make_float4(0.f, 0.f, 0.f, 0.f);
   int cur_wc = -1;                                      // MAC role: channel whose tap spectra are in shared memory
 
   for (int t = 0; t < total_steps + 2; ++t) {
@@ -223,6 +226,11 @@ k_chain_fft(const __grid_constant__ CUtensorMap tm_u, Geom g, State* __restrict_
         const int zr = task >> 3, tt = task & 7;
         const float* ra = IN + zr * C::INW + C::DX + tt;
         float2* dst = U + ((t & 1) * C::S + zr) * FFT_PITCH;
+        {   // the MAC role reads the image spectra of this step during the NEXT time step: bring them into L2 now
+          const ChainPiece pf = pieces[cf.p];
+          const float2* ipn = Ipk + (size_t(pf.ipk_row0) + size_t(cf.j) * C::S) * FFT_N + task * 16;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(ipn));
+        }
         fft128_core<false>(dst, tw, tt, [&](int j) { return make_float2(ra[8 * j], ra[C::S * C::INW + 8 * j]); }, 0xffffffffu, 0);
       }
       // slow path of the MAC role's step (t - 1): signal-domain masking of its residual rows
@@ -281,51 +289,49 @@ k_chain_fft(const __grid_constant__ CUtensorMap tm_u, Geom g, State* __restrict_
         const float2* w0 = WS + kk;
         const float2* w1 = WS + K * C::WP + kk;
         const float2* ip = Ipk + (size_t(pc.ipk_row0) + size_t(cm.j) * C::S) * FFT_N + k;
-        const bool conj = k > 64;
-        float2 iv[8];
-#pragma unroll
-        for (int y = 0; y < 8; ++y) iv[y] = __ldg(ip + size_t(y) * FFT_N);
+        const float sgn = (k > 64) ? -1.f : 1.f;
         // Err^ = 128 sum W0 U^ - I^, three blocks of 8 rows
-#define RLTV_CHAIN_MAC1(B)                                                                                         \
-        {                                                                                                          \
-          float2 acc[8];                                                                                           \
-          if (conj) chain_mac_block<K, 8 * B, true, FFT_N, FFT_PITCH>(utail, ucur, w0, acc);                       \
-          else chain_mac_block<K, 8 * B, false, FFT_N, FFT_PITCH>(utail, ucur, w0, acc);                           \
-          float2 nv[8];                                                                                            \
-          if (B < 2) {                                                                                             \
-            _Pragma("unroll") for (int y = 0; y < 8; ++y) nv[y] = __ldg(ip + size_t(8 * (B + 1) + y) * FFT_N);     \
-          }                                                                                                        \
-          _Pragma("unroll") for (int y = 0; y < 8; ++y)                                                            \
-            ecur[(8 * B + y) * FFT_N] = make_float2(acc[y].x - iv[y].x, acc[y].y - iv[y].y);                       \
-          if (B < 2) {                                                                                             \
-            _Pragma("unroll") for (int y = 0; y < 8; ++y) iv[y] = nv[y];                                           \
-          }                                                                                                        \
-        }
-        RLTV_CHAIN_MAC1(0)
-        RLTV_CHAIN_MAC1(1)
-        RLTV_CHAIN_MAC1(2)
-#undef RLTV_CHAIN_MAC1
-        // rows the next step needs from this block of U^ (the block itself is overwritten during the next step)
+        {
+          float2 z[8 + K - 1];
 #pragma unroll
-        for (int m = 0; m < C::T2; ++m) utail[m * FFT_N] = ucur[(C::S - C::T2 + m) * FFT_PITCH];
+          for (int m = 0; m < C::T2; ++m) z[m] = utail[m * FFT_N];
+#pragma unroll 1
+          for (int B = 0; B < C::S / 8; ++B) {
+            float2 iv[8];
+#pragma unroll
+            for (int y = 0; y < 8; ++y) iv[y] = __ldg(ip + size_t(8 * B + y) * FFT_N);   // L2 hits: prefetched one step ahead
+            float2 acc[8];
+            chain_mac_block<K, FFT_PITCH>(z, ucur + 8 * B * FFT_PITCH, w0, sgn, acc);
+#pragma unroll
+            for (int y = 0; y < 8; ++y) ecur[(8 * B + y) * FFT_N] = make_float2(acc[y].x - iv[y].x, acc[y].y - iv[y].y);
+#pragma unroll
+            for (int m = 0; m < C::T2; ++m) z[m] = z[m + 8];
+          }
+          // rows the next step needs from this block of U^ (the block itself is overwritten during the next step)
+#pragma unroll
+          for (int m = 0; m < C::T2; ++m) utail[m * FFT_N] = z[m];
+        }
         if (needs_fix(pc, cm.j)) {
           named_bar_arrive(1, C::NMAC + C::NFFT);
           named_bar_sync(2, C::NMAC + C::NFFT);
         }
         // G^ = sum W1 Err^
-#define RLTV_CHAIN_MAC2(B)                                                                                         \
-        {                                                                                                          \
-          float2 acc[8];                                                                                           \
-          if (conj) chain_mac_block<K, 8 * B, true, FFT_N, FFT_N>(etail, ecur, w1, acc);                           \
-          else chain_mac_block<K, 8 * B, false, FFT_N, FFT_N>(etail, ecur, w1, acc);                               \
-          _Pragma("unroll") for (int y = 0; y < 8; ++y) gb[(8 * B + y) * FFT_PITCH] = acc[y];                      \
-        }
-        RLTV_CHAIN_MAC2(0)
-        RLTV_CHAIN_MAC2(1)
-        RLTV_CHAIN_MAC2(2)
-#undef RLTV_CHAIN_MAC2
+        {
+          float2 z[8 + K - 1];
 #pragma unroll
-        for (int m = 0; m < C::T2; ++m) etail[m * FFT_N] = ecur[(C::S - C::T2 + m) * FFT_N];
+          for (int m = 0; m < C::T2; ++m) z[m] = etail[m * FFT_N];
+#pragma unroll 1
+          for (int B = 0; B < C::S / 8; ++B) {
+            float2 acc[8];
+            chain_mac_block<K, FFT_N>(z, ecur + 8 * B * FFT_N, w1, sgn, acc);
+#pragma unroll
+            for (int y = 0; y < 8; ++y) gb[(8 * B + y) * FFT_PITCH] = acc[y];
+#pragma unroll
+            for (int m = 0; m < C::T2; ++m) z[m] = z[m + 8];
+          }
+#pragma unroll
+          for (int m = 0; m < C::T2; ++m) etail[m * FFT_N] = z[m];
+        }
       }
     } else {
       // ---------------- inverse FFT + epilogue of step t - 2 ----------------
@@ -337,37 +343,9 @@ k_chain_fft(const __grid_constant__ CUtensorMap tm_u, Geom g, State* __restrict_
         const bool va = rel >= 0 && rel < pc.L, vb = rel >= 0 && rel < pc.Lb;
         float2* row = GB + (((t - 2) & 1) * C::S + zr) * FFT_PITCH;
         const int xs = C::V * pc.s;
-        // operands of the statistics first: their DRAM latency hides behind the inverse FFT
-        constexpr int NQ = (C::V / 4 + 7) / 8;
-        float4 da[NQ], db[NQ];                                       // (u - ut) / 2
         const size_t offa = size_t(pc.c) * g.plane + size_t(va ? ya : 0) * g.pitch + xs;
         const size_t offb = size_t(pc.c) * g.plane + size_t(vb ? yb : 0) * g.pitch + xs;
-#pragma unroll
-        for (int q = 0; q < NQ; ++q) {
-          const int x4 = 4 * (tt + 8 * q);
-          const bool ok = x4 < C::V && xs + x4 < g.pitch;
-          da[q] = db[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ok && va) {
-            const float4 u4 = __ldg(reinterpret_cast<const float4*>(ug + offa + x4));
-            const float4 t4 = ut_is_u ? u4 : __ldg(reinterpret_cast<const float4*>(utg + offa + x4));
-            da[q] = make_float4(0.5f * (u4.x - t4.x), 0.5f * (u4.y - t4.y), 0.5f * (u4.z - t4.z), 0.5f * (u4.w - t4.w));
-            const int Xm = xs + x4;
-            if (Xm < g.Wu) mu = fmaxf(mu, u4.x);
-            if (Xm + 1 < g.Wu) mu = fmaxf(mu, u4.y);
-            if (Xm + 2 < g.Wu) mu = fmaxf(mu, u4.z);
-            if (Xm + 3 < g.Wu) mu = fmaxf(mu, u4.w);
-          }
-          if (ok && vb) {
-            const float4 u4 = __ldg(reinterpret_cast<const float4*>(ug + offb + x4));
-            const float4 t4 = ut_is_u ? u4 : __ldg(reinterpret_cast<const float4*>(utg + offb + x4));
-            db[q] = make_float4(0.5f * (u4.x - t4.x), 0.5f * (u4.y - t4.y), 0.5f * (u4.z - t4.z), 0.5f * (u4.w - t4.w));
-            const int Xm = xs + x4;
-            if (Xm < g.Wu) mu = fmaxf(mu, u4.x);
-            if (Xm + 1 < g.Wu) mu = fmaxf(mu, u4.y);
-            if (Xm + 2 < g.Wu) mu = fmaxf(mu, u4.z);
-            if (Xm + 3 < g.Wu) mu = fmaxf(mu, u4.w);
-          }
-        }
+        // (u - ut)/2 of this row pair is already in da / db: loaded during the previous time step, see below
         fft128_core<true>(row, tw, tt, [&](int j) { return row[tt + 8 * j]; }, 0xffffffffu, 0);
         __syncwarp();
 #pragma unroll
@@ -412,6 +390,58 @@ k_chain_fft(const __grid_constant__ CUtensorMap tm_u, Geom g, State* __restrict_
     if (t >= 2) advance(ci);
     if (t >= 1 && t <= total_steps) advance(cm);
     if (t < total_steps) advance(cf);
+    // inverse-FFT role: operands of the statistics of its NEXT row pair (u, ut under the g rows of step t - 1), so that
+    // their DRAM latency is spent behind the barrier and the next inverse FFT instead of in front of the epilogue
+    if (warp >= 4 && warp < 10 && t >= 1 && t <= total_steps) {
+      const ChainPiece pc = pieces[ci.p];
+      const int task = tid - 128, zr = task >> 3, tt = task & 7;
+      const int rel = ci.j * C::S - 4 * C::P + zr;
+      const int ya = pc.ya + rel, yb = ya + pc.L;
+      const bool va = rel >= 0 && rel < pc.L, vb = rel >= 0 && rel < pc.Lb;
+      const int xs = C::V * pc.s;
+      const size_t offa = size_t(pc.c) * g.plane + size_t(va ? ya : 0) * g.pitch + xs;
+      const size_t offb = size_t(pc.c) * g.plane + size_t(vb ? yb : 0) * g.pitch + xs;
+      // all loads of a batch are issued before any is consumed (clamped addresses instead of branches: with a branch
+      // per load the compiler serialised eight DRAM round trips per step and this role became the critical path)
+      constexpr int QB = (NQ + 1) / 2;
+#pragma unroll
+      for (int q0 = 0; q0 < NQ; q0 += QB) {
+        float4 ua[QB], ta[QB], ub[QB], tb[QB];
+#pragma unroll
+        for (int i = 0; i < QB; ++i) {
+          const int q = q0 + i;
+          const int x4 = 4 * (tt + 8 * q);
+          const bool ok = q < NQ && x4 < C::V && xs + x4 < g.pitch;
+          const int xc = ok ? x4 : 0;
+          ua[i] = __ldg(reinterpret_cast<const float4*>(ug + offa + xc));
+          ub[i] = __ldg(reinterpret_cast<const float4*>(ug + offb + xc));
+          if (!ut_is_u) {
+            ta[i] = __ldg(reinterpret_cast<const float4*>(utg + offa + xc));
+            tb[i] = __ldg(reinterpret_cast<const float4*>(utg + offb + xc));
+          } else {
+            ta[i] = ua[i];
+            tb[i] = ub[i];
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < QB; ++i) {
+          const int q = q0 + i;
+          if (q >= NQ) continue;
+          const int x4 = 4 * (tt + 8 * q);
+          const bool ok = x4 < C::V && xs + x4 < g.pitch;
+          const int Xm = xs + x4;
+          const bool c0 = ok && Xm < g.Wu, c1 = ok && Xm + 1 < g.Wu, c2 = ok && Xm + 2 < g.Wu, c3 = ok && Xm + 3 < g.Wu;
+          da[q] = make_float4(0.5f * (ua[i].x - ta[i].x), 0.5f * (ua[i].y - ta[i].y), 0.5f * (ua[i].z - ta[i].z), 0.5f * (ua[i].w - ta[i].w));
+          db[q] = make_float4(0.5f * (ub[i].x - tb[i].x), 0.5f * (ub[i].y - tb[i].y), 0.5f * (ub[i].z - tb[i].z), 0.5f * (ub[i].w - tb[i].w));
+          if (va) {
+            mu = fmaxf(mu, fmaxf(fmaxf(c0 ? ua[i].x : -INFINITY, c1 ? ua[i].y : -INFINITY), fmaxf(c2 ? ua[i].z : -INFINITY, c3 ? ua[i].w : -INFINITY)));
+          }
+          if (vb) {
+            mu = fmaxf(mu, fmaxf(fmaxf(c0 ? ub[i].x : -INFINITY, c1 ? ub[i].y : -INFINITY), fmaxf(c2 ? ub[i].z : -INFINITY, c3 ? ub[i].w : -INFINITY)));
+          }
+        }
+      }
+    }
     __syncthreads();
     // the TMA stage was consumed by the forward FFT of step t: load step t + 1
     if (tid == 0 && t + 1 < total_steps) issue(pieces[cf.p], cf.j);

@@ -31,9 +31,10 @@ struct State {
   int it;                  // outer iterations executed (pyx:456,:656)
   int blind_steps;         // PSF steps taken (for the `correlation` caller-array quirk, pyx:581-585)
   float M_r, M_r_prev;     // pyx:624,:638
-  int max_u[3];            // order-preserving int encoding of max(u_c)           (pyx:524)
-  int max_G[3];            //                                 max|gradu_c|        (pyx:524)
-                           // (6 contiguous int32: one MAX all-reduce across row bands)
+  int smax[2][6];          // step statistics, order-preserving int encoding: [slot][0..2] = max(u_c), [slot][3..5] = max|gradu_c|
+                           // (pyx:524; 6 contiguous int32 = one MAX all-reduce across row bands).  Slot 0 is THE slot of
+                           // the two-kernel gradient path (reset by its forward kernel); the chain kernel alternates
+                           // the slots by inner step and the update kernel resets the one the next step will use.
   float dt[3];             // last image step sizes
   float dtpsf;             // last PSF step size (pyx:574)
   double win_sum;          // whiteness window: sum, min, max of the residual (pyx:627-629)

@@ -6,6 +6,15 @@
 
 namespace rltv {
 
+// Start of a solve: both statistics slots empty (State was zeroed just before).
+__global__ void k_state_init(State* __restrict__ st) {
+  if (threadIdx.x < 6) {
+    const int s = threadIdx.x / 3, c = threadIdx.x % 3;
+    st->smax[s][c] = ORD_LOWEST;
+    st->smax[s][3 + c] = 0;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // K3: u -= dt_c * (lambda*g + (u-ut)/2) on the whole padded domain (pyx:519-531), then on the interior
 //     DoF = ((g - I)/(g + I))^2 [/lambda if non-blind] ; u = (1-DoF)*u + DoF*I          (pyx:499-502, :552)
@@ -13,14 +22,21 @@ namespace rltv {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_update(Geom g, State* __restrict__ st, float* __restrict__ u, const float* __restrict__ ut,
-         const float* __restrict__ gbuf, const float* __restrict__ img, float step, float lambd, int blind) {
+         const float* __restrict__ gbuf, const float* __restrict__ img, float step, float lambd, int blind,
+         int slot, int reset_slot) {
   if (st->stop) return;
   const int c = blockIdx.z;
   const int Y = g.own0 + blockIdx.y;          // only owned rows are updated; halo rows arrive from the neighbours
   const int X = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
   // dt = step_factor * (amax(u_c) + 0) / (amax|gradu_c| + 1e-15), float32 like the reference (pyx:524)
-  const float dt = step * ord2f(st->max_u[c]) / (ord2f(st->max_G[c]) + 1e-15f);
-  if (X == 0 && blockIdx.y == 0) st->dt[c] = dt;
+  const float dt = step * ord2f(st->smax[slot][c]) / (ord2f(st->smax[slot][3 + c]) + 1e-15f);
+  if (X == 0 && blockIdx.y == 0) {
+    st->dt[c] = dt;
+    if (reset_slot >= 0) {               // the statistics slot of the NEXT inner step (nobody touches it now)
+      st->smax[reset_slot][c] = ORD_LOWEST;
+      st->smax[reset_slot][3 + c] = 0;
+    }
+  }
   if (X >= g.Wu) return;
   const size_t off = size_t(c) * g.plane + size_t(Y) * g.pitch + X;
   const float4 uv = *reinterpret_cast<const float4*>(u + off);

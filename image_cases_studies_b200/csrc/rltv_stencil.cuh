@@ -162,8 +162,8 @@ k_conv(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtens
 
   if (!ADJ && blockIdx.x == 0 && tid < 3) {
     // first kernel of an inner step: reset the step-size reductions the adjoint kernel accumulates into
-    st->max_u[tid] = ORD_LOWEST;
-    st->max_G[tid] = 0;
+    st->smax[0][tid] = ORD_LOWEST;
+    st->smax[0][3 + tid] = 0;
   }
   if (tid == 0) {
     mbar_init(&bars[0], 1);
@@ -268,8 +268,8 @@ k_conv(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtens
           a = warp_max(a);
           b = warp_max(b);
           if (lane == 0) {
-            atomicMax(&st->max_u[c], f2ord(a));
-            atomicMax(&st->max_G[c], f2ord(b));
+            atomicMax(&st->smax[0][c], f2ord(a));
+            atomicMax(&st->smax[0][3 + c], f2ord(b));
           }
         }
         __syncthreads();

@@ -96,8 +96,8 @@ k_conv_fft(const __grid_constant__ CUtensorMap tm_in, const float* __restrict__ 
   const int tiles_per_c = ntx * nty, ntiles = 3 * tiles_per_c;
 
   if (!ADJ && blockIdx.x == 0 && tid < 3) {
-    st->max_u[tid] = ORD_LOWEST;
-    st->max_G[tid] = 0;
+    st->smax[0][tid] = ORD_LOWEST;
+    st->smax[0][3 + tid] = 0;
   }
   if (tid == 0) {
     mbar_init(bar, 1);
@@ -287,8 +287,8 @@ k_conv_fft(const __grid_constant__ CUtensorMap tm_in, const float* __restrict__ 
           a = warp_max(a);
           b = warp_max(b);
           if (lane == 0) {
-            atomicMax(&st->max_u[c], f2ord(a));
-            atomicMax(&st->max_G[c], f2ord(b));
+            atomicMax(&st->smax[0][c], f2ord(a));
+            atomicMax(&st->smax[0][3 + c], f2ord(b));
           }
         }
         __syncthreads();

@@ -158,6 +158,14 @@ class Solver:
         nat.check(nat.lib.rltv_stage_adjoint(self._ctx, nat.ptr(out)))
         return out
 
+    def stage_chain(self):
+        """g = adjoint(forward residual) from the spectral chain kernel, and the step statistics it reduces
+        (max u_c, max |g_c|): returns (g, max6)."""
+        out = np.empty(self.u_shape, np.float32)
+        mx = np.empty(6, np.float32)
+        nat.check(nat.lib.rltv_stage_chain(self._ctx, nat.ptr(out), nat.ptr(mx)))
+        return out, mx
+
     def stage_gradk(self) -> np.ndarray:
         out = np.empty((self.MK, self.MK, 3), np.float32)
         nat.check(nat.lib.rltv_stage_gradk(self._ctx, nat.ptr(out)))

@@ -159,6 +159,10 @@ int rltv_poll_wait(rltv_ctx* ctx, int32_t it, int32_t* stop);
 int rltv_stage_residual(rltv_ctx* ctx, float* err_out /* packed HWC (M,N,3) */);
 /* g = full-conv(err, rot180(psf)) on the u domain (pyx:490-491), using the residual currently on device */
 int rltv_stage_adjoint(rltv_ctx* ctx, float* g_out /* packed HWC (M+MK-1, N+MK-1, 3) */);
+/* Spectral chain kernel (11 <= MK <= 17, csrc/rltv_chain_fft.cuh): g = full-conv(valid-conv(u, psf) - image, rot180(psf))
+ * (pyx:477-491) in one pass from u, psf and the image on the device; also returns the step statistics it reduces,
+ * max(u_c) and max|g_c| per channel (pyx:524 with lambda = 1 and ut = u).  RLTV_ERR_STATE if the context does not use it. */
+int rltv_stage_chain(rltv_ctx* ctx, float* g_out /* packed HWC (M+MK-1, N+MK-1, 3) */, float* max6 /* 6 floats or NULL */);
 /* gk = valid-conv(rot180(u), err) (pyx:567-571).  Direct kernels / MK > 17: uses the residual currently on device
  * (call rltv_stage_residual first).  Row-FFT kernels, MK <= 17: the kernel computes the residual of pyx:557-565
  * itself from u, psf and the image and leaves it on the device (read it with rltv_debug_download_err). */

@@ -365,3 +365,31 @@ def test_row_fft_solver_against_oracle(dc, monkeypatch):
         assert np.allclose(st["M_r_history"], ref.M_r, rtol=2e-5)
     finally:
         dc.clear_cache()
+
+
+@pytest.mark.parametrize("K", [11, 13, 15, 17])
+@pytest.mark.parametrize("shape", [(5, 9), (61, 97), (100, 100), (203, 251), (331, 420)])
+def test_chain_kernel_against_oracle(K, shape):
+    """k_chain_fft (csrc/rltv_chain_fft.cuh): forward blur, residual and adjoint in one pass with the residual kept in
+    the row-frequency domain, against the float64 definition  g = conv(conv(u, psf, 'valid') - image, rot180 psf, 'full')
+    (pyx:477-491) and its own step statistics (pyx:524 with lambda = 1, ut = u).  Shapes: smaller than one segment,
+    around one segment (V = 128 - 2(K-1) columns), several segments and several 24-row steps per piece."""
+    from image_cases_studies_b200.solver import Solver
+    from oracle import rl_mm_oracle as orc
+    M, N = shape
+    rng = np.random.default_rng(7000 + 100 * K + M)
+    u = (0.1 + 0.8 * rng.random((M + K - 1, N + K - 1, 3))).astype(np.float32)
+    psf = rng.random((K, K, 3), dtype=np.float32)
+    psf /= psf.sum(axis=(0, 1), keepdims=True)
+    image = np.stack([orc.conv2(u[..., c], psf[..., c], "valid") for c in range(3)], axis=2)
+    image = (image * (1.0 + 0.05 * rng.standard_normal(image.shape))).astype(np.float32)
+    s = Solver(M, N, K)
+    s.upload(image, u, psf)
+    g, mx = s.stage_chain()
+    s.close()
+    for c in range(3):
+        e_ref = orc.conv2(u[..., c], psf[..., c], "valid") - image[..., c]
+        g_ref = orc.conv2(e_ref, orc.rot180(psf[..., c]), "full")
+        assert rel_l2(g[..., c], g_ref) < 2e-5, (c, rel_l2(g[..., c], g_ref))
+        assert abs(mx[c] - u[..., c].max()) == 0
+        assert abs(mx[3 + c] - np.abs(g_ref).max()) <= 1e-4 * np.abs(g_ref).max()
