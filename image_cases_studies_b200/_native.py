@@ -6,12 +6,14 @@ if no CUDA device is present every compute call raises RuntimeError.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 import numpy as np
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "librltv_b200.so"
+# RLTV_LIB: an alternative build of the same library (kernel experiments, e.g. another warp-role split); never a fallback
+LIB_PATH = Path(os.environ["RLTV_LIB"]) if os.environ.get("RLTV_LIB") else PKG / "librltv_b200.so"
 
 RLTV_MAX_HISTORY = 4096
 RLTV_MAX_MK = 31
@@ -77,6 +79,7 @@ SYMBOLS = [
     ("rltv_poll_wait", C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]),
     ("rltv_stage_residual", C.c_int, [C.c_void_p, C.c_void_p]),
     ("rltv_stage_adjoint", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("rltv_debug_chain_roles", C.c_int, [C.c_int32]),
     ("rltv_stage_chain", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     ("rltv_stage_gradk", C.c_int, [C.c_void_p, C.c_void_p]),
     ("rltv_debug_download_err", C.c_int, [C.c_void_p, C.c_void_p]),

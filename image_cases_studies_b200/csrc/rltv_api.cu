@@ -1305,6 +1305,12 @@ int rltv_stage_tv(rltv_ctx* c, int32_t order, int32_t norm, float epsilon, float
   return RLTV_OK;
 }
 
+// Debug: skip roles of the chain kernel (bit mask, see g_chain_skip_roles) -- timing experiments only.
+int rltv_debug_chain_roles(int32_t mask) {
+  CU(cudaMemcpyToSymbol(g_chain_skip_roles, &mask, sizeof(int)));
+  return RLTV_OK;
+}
+
 // Debug: per-phase cycle totals of k_conv_fft since the last call (thread 0 of every CTA), then reset.
 int rltv_debug_phase_cycles(uint64_t* out8) {
   unsigned long long h[8] = {0};

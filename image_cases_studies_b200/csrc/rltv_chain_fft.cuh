@@ -16,12 +16,13 @@
 // spectra cannot express.  Only the first and last segment of a row and the first / last P rows of the frame are
 // affected; those steps take a slower path that drops to the signal domain once (inverse FFT, mask, forward FFT).
 //
-// One CTA per SM, 16 warps with fixed roles, ONE block barrier per step (software pipeline over steps t):
-//   warps 10-15  forward FFT of the u rows of step t      TMA stage -> U block (t & 1)
-//   warps  0-3   MAC of step t-1: thread = frequency bin; Err^ and G^ of 24 packed rows (1440 FFMA2 per thread);
-//                everything this role reads from the previous step (last 2P rows of U^ and Err^) and the whole Err^
-//                block are PRIVATE columns of shared memory: no synchronisation inside the role
-//   warps  4-9   inverse FFT of the g rows of step t-2 + epilogue (g store, step statistics), row-local
+// One CTA per SM, 20 warps with fixed roles, ONE block barrier per step (software pipeline over steps t):
+//   warps 14-19  forward FFT of the u rows of step t      TMA stage -> U block (t & 1)
+//   warps  0-7   MAC of step t-1: thread = (frequency bin, half of the step's 24 packed rows): Err^ then G^, 720 FFMA2
+//                per thread; two warps per scheduler so that one's window loads / stores hide behind the other's FMAs;
+//                the two halves meet at two 256-thread named barriers (Err^ complete / carried rows free)
+//   warps  8-13  inverse FFT of the g rows of step t-2 + epilogue (g store, step statistics), row-local; its u / ut
+//                operands are prefetched into L2 one time step ahead
 // The FMA pipe is the bound (MAC role: 2880 pipe cycles per step and SM sub-partition, FFT roles ~1000).
 #pragma once
 #include "rltv_band.cuh"
@@ -49,8 +50,16 @@ struct ChainCfg {
   static constexpr int DX = (4 - ((K - 1) & 3)) & 3;        // FFT sample n sits at TMA box column n + DX (16-byte aligned box start)
   static constexpr int S = 24;                              // packed rows per step
   static constexpr int INW = 136;                           // TMA box width (floats): rows start 8 banks apart
-  static constexpr int THREADS = 512;
-  static constexpr int NMAC = 128, NIFFT = 192, NFFT = 192; // role sizes (threads)
+#ifndef RLTV_CHAIN_WMAC
+#define RLTV_CHAIN_WMAC 4
+#endif
+  static constexpr int WMAC = RLTV_CHAIN_WMAC, WIFFT = 6, WFFT = 6;   // warps per role (WMAC = 4: one MAC thread per bin, 8: two)
+  static constexpr int THREADS = 32 * (WMAC + WIFFT + WFFT);
+  static constexpr int NMAC = 32 * WMAC, NIFFT = 32 * WIFFT, NFFT = 32 * WFFT; // role sizes (threads)
+  static constexpr int MH = WMAC / 4;                       // MAC threads per frequency bin
+  static constexpr int MROWS = S / MH;                      // rows of a step owned by one MAC thread
+  static constexpr int MR = (MH == 1) ? 8 : 6;              // MAC role: rows per register block
+  static constexpr int PCACHE = 24;                         // pieces of this CTA kept in shared memory
   static constexpr int T2 = 2 * P;                          // rows carried from one step to the next
   static constexpr int WP = 65;                             // tap spectra are Hermitian: bins 0..64 are stored
   static constexpr int U_BYTES = 2 * S * FFT_PITCH * 8;     // two blocks written by the forward FFT role
@@ -68,6 +77,7 @@ struct ChainCfg {
   static_assert(OFF_IN % 128 == 0, "TMA destination alignment");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
   static_assert(T2 <= S, "the carried rows come from one block");
+  static_assert(MROWS % MR == 0 && T2 % 2 == 0 && NIFFT == 8 * S && NFFT == 8 * S && (WMAC == 4 || WMAC == 8), "role geometry");
 };
 
 __host__ __device__ inline int chain_nseg(int Wu, int V) { return (Wu + V - 1) / V; }
@@ -122,28 +132,38 @@ __device__ __forceinline__ void named_bar_sync(int id, int count) {
 __device__ __forceinline__ void named_bar_arrive(int id, int count) {
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
+__device__ __forceinline__ float4 lds128(const void* p) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+  return v;
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-// MAC over one 8-row block with a ROLLING register window:  acc[y] = sum_ky w[ky] * z[y + ky], where z[0 .. 2P) are the
-// last 2P window rows of the previous block (or the rows carried over from the previous step) and z[2P .. 2P + 8) the
-// block's own 8 rows, loaded here.  On return the window has moved down by 8 rows.  The loop over the three blocks of
-// a step is NOT unrolled: a MAC warp runs alone on its scheduler, and straight-line code of a whole step (~30 KB) made
-// the role instruction-fetch bound (ncu: 'no instruction' was its top stall); one block body fits the L0 cache.
-template <int K, int CPITCH>
-__device__ __forceinline__ void chain_mac_block(float2 (&z)[8 + K - 1], const float2* __restrict__ cur,
-                                                const float2* __restrict__ w, float sgn, float2 (&acc)[8]) {
+// MAC over one block of R rows with a ROLLING register window:  acc[y] = sum_ky w[ky] * z[y + ky], where z[0 .. 2P) are
+// the last 2P window rows of the previous block (or the rows carried over from the previous step) and z[2P .. 2P + R)
+// the block's own rows, loaded here.  The caller moves the window down by R rows afterwards.  The loop over the blocks
+// of a step is NOT unrolled: straight-line code of a whole step (~30 KB) made the role instruction-fetch bound (ncu:
+// 'no instruction' was its top stall); one block body fits the L0 instruction cache.
+template <int K, int R, int CPITCH>
+__device__ __forceinline__ void chain_mac_block(float2 (&z)[R + K - 1], const float2* __restrict__ cur,
+                                                const float2* __restrict__ w, float sgn, float2 (&acc)[R]) {
   using C = ChainCfg<K>;
 #pragma unroll
-  for (int m = 0; m < 8; ++m) z[C::T2 + m] = cur[m * CPITCH];
+  for (int m = 0; m < R; ++m) z[C::T2 + m] = cur[m * CPITCH];
 #pragma unroll
-  for (int y = 0; y < 8; ++y) acc[y] = make_float2(0.f, 0.f);
+  for (int y = 0; y < R; ++y) acc[y] = make_float2(0.f, 0.f);
 #pragma unroll
   for (int ky = 0; ky < K; ++ky) {
     float2 wv = w[ky * C::WP];
     wv.y *= sgn;                       // bins above 64 read the spectrum of bin 128 - k: conjugate (real taps)
 #pragma unroll
-    for (int y = 0; y < 8; ++y) acc[y] = cfma(z[y + ky], wv, acc[y]);
+    for (int y = 0; y < R; ++y) acc[y] = cfma(z[y + ky], wv, acc[y]);
   }
 }
+
+// Debug: bit mask of roles whose work is skipped (1 forward FFT, 2 MAC, 4 inverse FFT + epilogue, 8 TMA loads); results
+// are garbage then -- used only to time the roles in isolation (rltv_debug_chain_roles).
+__device__ int g_chain_skip_roles = 0;
 
 struct ChainCursor {   // (piece, step) of one role; advanced once per time step
   int p, j;
@@ -156,7 +176,7 @@ struct ChainCursor {   // (piece, step) of one role; advanced once per time step
 template <int K>
 __global__ void __launch_bounds__(ChainCfg<K>::THREADS, 1)
 k_chain_fft(const __grid_constant__ CUtensorMap tm_u, Geom g, State* __restrict__ st, const float2* __restrict__ wspec,
-            const float2* __restrict__ Ipk, const ChainPiece* __restrict__ pieces, const int* __restrict__ cta_first,
+            const float2* __restrict__ Ipk, const ChainPiece* __restrict__ pieces_g, const int* __restrict__ cta_first,
             const float* __restrict__ ug, const float* __restrict__ utg, float lambd, float* __restrict__ gout,
             int slot, int ut_is_u, CommPeers cp, int seq, unsigned* __restrict__ done_counter) {
   using C = ChainCfg<K>;
@@ -186,8 +206,15 @@ k_chain_fft(const __grid_constant__ CUtensorMap tm_u, Geom g, State* __restrict_
   fft_fill_twiddles(tw);
   __syncthreads();
 
+  // this CTA's pieces in shared memory: with 220 KB of dynamic shared memory there is next to no L1 left, and every
+  // role reads the current piece several times per step (ncu: those L2 round trips were the top long-scoreboard stall)
+  __shared__ ChainPiece spc[C::PCACHE];
+  for (int i = tid; i < C::PCACHE && p0 + i < p1; i += C::THREADS) spc[i] = pieces_g[p0 + i];
+  __syncthreads();
+  auto piece_nsteps = [&](int p) { return (p - p0 < C::PCACHE) ? spc[p - p0].nsteps : pieces_g[p].nsteps; };
+  auto piece = [&](int p) -> ChainPiece { return (p - p0 < C::PCACHE) ? spc[p - p0] : pieces_g[p]; };
   int total_steps = 0;
-  for (int p = p0; p < p1; ++p) total_steps += pieces[p].nsteps;
+  for (int p = p0; p < p1; ++p) total_steps += piece_nsteps(p);
   const int imgLo = C::P - g.row0, imgHi = C::P + g.M - g.row0;       // local rows on which the residual exists
 
   // TMA of the u rows of (piece, step): real rows [ya - 2P + jS, +S) and the same of the second half
@@ -199,7 +226,7 @@ k_chain_fft(const __grid_constant__ CUtensorMap tm_u, Geom g, State* __restrict_
     tma_load_3d(smem + C::OFF_IN + C::S * C::INW * 4, &tm_u, xb, y + pc.L, pc.c, bar);
   };
   auto advance = [&](ChainCursor& cur) {
-    if (++cur.j >= pieces[cur.p].nsteps) { cur.j = 0; ++cur.p; }
+    if (++cur.j >= piece_nsteps(cur.p)) { cur.j = 0; ++cur.p; }
   };
   // a step needs the slow (masking) path if its residual rows touch rows outside the image or the segment is a border one
   auto needs_fix = [&](const ChainPiece& pc, int j) {
@@ -209,36 +236,46 @@ k_chain_fft(const __grid_constant__ CUtensorMap tm_u, Geom g, State* __restrict_
   };
 
   ChainCursor cf{p0, 0}, cm{p0, 0}, ci{p0, 0};          // forward FFT / MAC / inverse FFT cursors
-  if (tid == 0) issue(pieces[p0], 0);
+  const int skip = g_chain_skip_roles;
+  if (tid == 0 && !(skip & 8)) issue(piece(p0), 0);
   float mu = -INFINITY, mG = 0.f;                       // inverse-FFT role: statistics of the current piece's channel
   constexpr int NQ = (C::V / 4 + 7) / 8;                // float4 columns per thread of a row's 8-thread group
   float4 da[NQ], db[NQ];                                // inverse-FFT role: (u - ut)/2 under its next g row pair
 #pragma unroll
   for (int q = 0; q < NQ; ++q) da[q] = db[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+  constexpr int RB = C::MR;                             // MAC role: rows per block
   int cur_wc = -1;                                      // MAC role: channel whose tap spectra are in shared memory
+  // MAC role: thread = (frequency bin k, half h of the step's rows)
+  const int mk = tid & (FFT_N - 1), mh = (C::MH == 1) ? 0 : ((tid >> 7) & 1), mr0 = mh * C::MROWS;
+  float2 iv[RB];                                        // image spectra of the thread's next block (loaded one block ahead)
+#pragma unroll
+  for (int y = 0; y < RB; ++y) iv[y] = make_float2(0.f, 0.f);
+  if (warp < C::WMAC) {
+    const float2* ip = Ipk + (size_t(piece(p0).ipk_row0) + mr0) * FFT_N + mk;
+#pragma unroll
+    for (int y = 0; y < RB; ++y) iv[y] = __ldg(ip + size_t(y) * FFT_N);
+  }
 
   for (int t = 0; t < total_steps + 2; ++t) {
-    if (warp >= 10) {
+    if (warp >= C::WMAC + C::WIFFT) {
       // ---------------- forward FFT of step t ----------------
-      if (t < total_steps) {
-        mbar_wait(bar, t & 1);
-        const int task = tid - 320;                      // 0..191: row = task >> 3
-        const int zr = task >> 3, tt = task & 7;
+      const int task = tid - 32 * (C::WMAC + C::WIFFT);  // 0..191: row = task >> 3
+      const int zr = task >> 3, tt = task & 7;
+      if (t < total_steps && !(skip & 1)) {
+        {   // the MAC role reads the image spectra of this step during the NEXT time step: bring them into L2 now
+          const ChainPiece pf = piece(cf.p);
+          prefetch_l2(Ipk + (size_t(pf.ipk_row0) + size_t(cf.j) * C::S) * FFT_N + task * 16);
+        }
+        if (!(skip & 8)) mbar_wait(bar, t & 1);
         const float* ra = IN + zr * C::INW + C::DX + tt;
         float2* dst = U + ((t & 1) * C::S + zr) * FFT_PITCH;
-        {   // the MAC role reads the image spectra of this step during the NEXT time step: bring them into L2 now
-          const ChainPiece pf = pieces[cf.p];
-          const float2* ipn = Ipk + (size_t(pf.ipk_row0) + size_t(cf.j) * C::S) * FFT_N + task * 16;
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(ipn));
-        }
         fft128_core<false>(dst, tw, tt, [&](int j) { return make_float2(ra[8 * j], ra[C::S * C::INW + 8 * j]); }, 0xffffffffu, 0);
       }
       // slow path of the MAC role's step (t - 1): signal-domain masking of its residual rows
       if (t >= 1 && t <= total_steps) {
-        const ChainPiece pc = pieces[cm.p];
+        const ChainPiece pc = piece(cm.p);
         if (needs_fix(pc, cm.j)) {
           named_bar_sync(1, C::NMAC + C::NFFT);          // MAC role has written Err^ of this step
-          const int task = tid - 320, zr = task >> 3, tt = task & 7;
           float2* scratch = GB + (((t - 1) & 1) * C::S + zr) * FFT_PITCH;   // G^ block of this step: not written yet
           const float2* erow = EC + zr * FFT_N;
           fft128_core<true>(scratch, tw, tt, [&](int j) { return erow[tt + 8 * j]; }, 0xffffffffu, 0);
@@ -263,11 +300,11 @@ k_chain_fft(const __grid_constant__ CUtensorMap tm_u, Geom g, State* __restrict_
           named_bar_sync(2, C::NMAC + C::NFFT);          // MAC role may read the masked Err^
         }
       }
-    } else if (warp < 4) {
-      // ---------------- MAC of step t - 1 ----------------
-      if (t >= 1 && t <= total_steps) {
-        const ChainPiece pc = pieces[cm.p];
-        const int k = tid, kk = (k <= 64) ? k : FFT_N - k;
+    } else if (warp < C::WMAC) {
+      // ---------------- MAC of step t - 1: thread = (bin mk, rows [mr0, mr0 + S/2) of the step) ----------------
+      if (t >= 1 && t <= total_steps && !(skip & 2)) {
+        const ChainPiece pc = piece(cm.p);
+        const int kk = (mk <= 64) ? mk : FFT_N - mk;
         if (pc.c != cur_wc) {
           // tap spectra of this channel: forward taps scaled by 128 (Err^ must be the unnormalised spectrum, like I^)
           named_bar_sync(3, C::NMAC);
@@ -281,35 +318,43 @@ k_chain_fft(const __grid_constant__ CUtensorMap tm_u, Geom g, State* __restrict_
           cur_wc = pc.c;
         }
         const int blk = (t - 1) & 1;
-        const float2* ucur = U + blk * C::S * FFT_PITCH + k;
-        float2* utail = UT + k;
-        float2* ecur = EC + k;
-        float2* etail = ET + k;
-        float2* gb = GB + blk * C::S * FFT_PITCH + k;
+        const float2* ucur = U + blk * C::S * FFT_PITCH + mk;
+        float2* utail = UT + mk;
+        float2* ecur = EC + mk;
+        float2* etail = ET + mk;
+        float2* gb = GB + blk * C::S * FFT_PITCH + mk;
         const float2* w0 = WS + kk;
         const float2* w1 = WS + K * C::WP + kk;
-        const float2* ip = Ipk + (size_t(pc.ipk_row0) + size_t(cm.j) * C::S) * FFT_N + k;
-        const float sgn = (k > 64) ? -1.f : 1.f;
-        // Err^ = 128 sum W0 U^ - I^, three blocks of 8 rows
+        const float2* ip = Ipk + (size_t(pc.ipk_row0) + size_t(cm.j) * C::S + mr0) * FFT_N + mk;
+        const float sgn = (mk > 64) ? -1.f : 1.f;
+        // Err^ = 128 sum W0 U^ - I^ on this thread's rows, blocks of RB rows
         {
-          float2 z[8 + K - 1];
+          float2 z[RB + K - 1];
 #pragma unroll
-          for (int m = 0; m < C::T2; ++m) z[m] = utail[m * FFT_N];
-#pragma unroll 1
-          for (int B = 0; B < C::S / 8; ++B) {
-            float2 iv[8];
-#pragma unroll
-            for (int y = 0; y < 8; ++y) iv[y] = __ldg(ip + size_t(8 * B + y) * FFT_N);   // L2 hits: prefetched one step ahead
-            float2 acc[8];
-            chain_mac_block<K, FFT_PITCH>(z, ucur + 8 * B * FFT_PITCH, w0, sgn, acc);
-#pragma unroll
-            for (int y = 0; y < 8; ++y) ecur[(8 * B + y) * FFT_N] = make_float2(acc[y].x - iv[y].x, acc[y].y - iv[y].y);
-#pragma unroll
-            for (int m = 0; m < C::T2; ++m) z[m] = z[m + 8];
+          for (int m = 0; m < C::T2; ++m) {
+            const int x = mr0 + m;                       // window row in [tail | current block]
+            z[m] = (x < C::T2) ? utail[x * FFT_N] : ucur[(x - C::T2) * FFT_PITCH];
           }
-          // rows the next step needs from this block of U^ (the block itself is overwritten during the next step)
+#pragma unroll 1
+          for (int B = 0; B < C::MROWS / RB; ++B) {
+            float2 acc[RB];
+            chain_mac_block<K, RB, FFT_PITCH>(z, ucur + (mr0 + RB * B) * FFT_PITCH, w0, sgn, acc);
 #pragma unroll
-          for (int m = 0; m < C::T2; ++m) utail[m * FFT_N] = z[m];
+            for (int y = 0; y < RB; ++y) ecur[(mr0 + RB * B + y) * FFT_N] = make_float2(acc[y].x - iv[y].x, acc[y].y - iv[y].y);
+            if (B + 1 < C::MROWS / RB) {                 // image spectra of the next block: L2 hits, one block of MACs to land
+#pragma unroll
+              for (int y = 0; y < RB; ++y) iv[y] = __ldg(ip + size_t(RB * (B + 1) + y) * FFT_N);
+            }
+#pragma unroll
+            for (int m = 0; m < C::T2; ++m) z[m] = z[m + RB];
+          }
+        }
+        if (C::MH > 1) named_bar_sync(4, C::NMAC);       // Err^ of the step complete; nobody reads the old U^ tail any more
+        // rows the next step needs from this block of U^ (the block itself is overwritten during the next step)
+#pragma unroll
+        for (int m = 0; m < C::T2 / C::MH; ++m) {
+          const int r = mh * (C::T2 / C::MH) + m;
+          utail[r * FFT_N] = ucur[(C::S - C::T2 + r) * FFT_PITCH];
         }
         if (needs_fix(pc, cm.j)) {
           named_bar_arrive(1, C::NMAC + C::NFFT);
@@ -317,27 +362,42 @@ k_chain_fft(const __grid_constant__ CUtensorMap tm_u, Geom g, State* __restrict_
         }
         // G^ = sum W1 Err^
         {
-          float2 z[8 + K - 1];
+          float2 z[RB + K - 1];
 #pragma unroll
-          for (int m = 0; m < C::T2; ++m) z[m] = etail[m * FFT_N];
-#pragma unroll 1
-          for (int B = 0; B < C::S / 8; ++B) {
-            float2 acc[8];
-            chain_mac_block<K, FFT_N>(z, ecur + 8 * B * FFT_N, w1, sgn, acc);
-#pragma unroll
-            for (int y = 0; y < 8; ++y) gb[(8 * B + y) * FFT_PITCH] = acc[y];
-#pragma unroll
-            for (int m = 0; m < C::T2; ++m) z[m] = z[m + 8];
+          for (int m = 0; m < C::T2; ++m) {
+            const int x = mr0 + m;
+            z[m] = (x < C::T2) ? etail[x * FFT_N] : ecur[(x - C::T2) * FFT_N];
           }
+#pragma unroll 1
+          for (int B = 0; B < C::MROWS / RB; ++B) {
+            float2 acc[RB];
+            chain_mac_block<K, RB, FFT_N>(z, ecur + (mr0 + RB * B) * FFT_N, w1, sgn, acc);
 #pragma unroll
-          for (int m = 0; m < C::T2; ++m) etail[m * FFT_N] = z[m];
+            for (int y = 0; y < RB; ++y) gb[(mr0 + RB * B + y) * FFT_PITCH] = acc[y];
+#pragma unroll
+            for (int m = 0; m < C::T2; ++m) z[m] = z[m + RB];
+          }
+        }
+        if (C::MH > 1) named_bar_sync(4, C::NMAC);       // nobody reads the old Err^ tail any more
+#pragma unroll
+        for (int m = 0; m < C::T2 / C::MH; ++m) {
+          const int r = mh * (C::T2 / C::MH) + m;
+          etail[r * FFT_N] = ecur[(C::S - C::T2 + r) * FFT_N];
+        }
+        // image spectra of this thread's first block of the NEXT step: in flight across the barrier
+        if (t < total_steps) {
+          ChainCursor nx = cm;
+          advance(nx);
+          const float2* ipn = Ipk + (size_t(piece(nx.p).ipk_row0) + size_t(nx.j) * C::S + mr0) * FFT_N + mk;
+#pragma unroll
+          for (int y = 0; y < RB; ++y) iv[y] = __ldg(ipn + size_t(y) * FFT_N);
         }
       }
     } else {
       // ---------------- inverse FFT + epilogue of step t - 2 ----------------
-      if (t >= 2) {
-        const ChainPiece pc = pieces[ci.p];
-        const int task = tid - 128, zr = task >> 3, tt = task & 7;
+      if (t >= 2 && !(skip & 4)) {
+        const ChainPiece pc = piece(ci.p);
+        const int task = tid - 32 * C::WMAC, zr = task >> 3, tt = task & 7;
         const int rel = ci.j * C::S - 4 * C::P + zr;                 // g row of the first half, relative to the piece
         const int ya = pc.ya + rel, yb = ya + pc.L;
         const bool va = rel >= 0 && rel < pc.L, vb = rel >= 0 && rel < pc.Lb;
@@ -345,7 +405,7 @@ k_chain_fft(const __grid_constant__ CUtensorMap tm_u, Geom g, State* __restrict_
         const int xs = C::V * pc.s;
         const size_t offa = size_t(pc.c) * g.plane + size_t(va ? ya : 0) * g.pitch + xs;
         const size_t offb = size_t(pc.c) * g.plane + size_t(vb ? yb : 0) * g.pitch + xs;
-        // (u - ut)/2 of this row pair is already in da / db: loaded during the previous time step, see below
+        // (u - ut)/2 under this row pair is already in da / db: loaded at the end of the previous time step (below)
         fft128_core<true>(row, tw, tt, [&](int j) { return row[tt + 8 * j]; }, 0xffffffffu, 0);
         __syncwarp();
 #pragma unroll
@@ -353,8 +413,8 @@ k_chain_fft(const __grid_constant__ CUtensorMap tm_u, Geom g, State* __restrict_
           const int x4 = 4 * (tt + 8 * q);
           const bool ok = x4 < C::V && xs + x4 < g.pitch;
           if (!ok) continue;
-          const float4 z01 = *reinterpret_cast<const float4*>(row + (K - 1) + x4);          // (re0, im0, re1, im1)
-          const float4 z23 = *reinterpret_cast<const float4*>(row + (K - 1) + x4 + 2);
+          const float4 z01 = lds128(row + (K - 1) + x4);            // (re0, im0, re1, im1)
+          const float4 z23 = lds128(row + (K - 1) + x4 + 2);
           const int Xm = xs + x4;
           const bool c0 = Xm < g.Wu, c1 = Xm + 1 < g.Wu, c2 = Xm + 2 < g.Wu, c3 = Xm + 3 < g.Wu;
           if (va) {
@@ -390,17 +450,36 @@ k_chain_fft(const __grid_constant__ CUtensorMap tm_u, Geom g, State* __restrict_
     if (t >= 2) advance(ci);
     if (t >= 1 && t <= total_steps) advance(cm);
     if (t < total_steps) advance(cf);
-    // inverse-FFT role: operands of the statistics of its NEXT row pair (u, ut under the g rows of step t - 1), so that
-    // their DRAM latency is spent behind the barrier and the next inverse FFT instead of in front of the epilogue
-    if (warp >= 4 && warp < 10 && t >= 1 && t <= total_steps) {
-      const ChainPiece pc = pieces[ci.p];
-      const int task = tid - 128, zr = task >> 3, tt = task & 7;
+    // inverse-FFT role, end of the time step: (a) load u / ut under its NEXT g row pair (step t - 1) and keep (u - ut)/2 in
+    // registers across the barrier -- the rows were prefetched into L2 one time step earlier, so this costs L2 latency;
+    // (b) prefetch the rows of the step after that into L2.
+    if (warp >= C::WMAC && warp < C::WMAC + C::WIFFT && t >= 1 && t <= total_steps && !(skip & 4)) {
+      const ChainPiece pc = piece(ci.p);
+      const int task = tid - 32 * C::WMAC, zr = task >> 3, tt = task & 7;
       const int rel = ci.j * C::S - 4 * C::P + zr;
       const int ya = pc.ya + rel, yb = ya + pc.L;
       const bool va = rel >= 0 && rel < pc.L, vb = rel >= 0 && rel < pc.Lb;
       const int xs = C::V * pc.s;
       const size_t offa = size_t(pc.c) * g.plane + size_t(va ? ya : 0) * g.pitch + xs;
       const size_t offb = size_t(pc.c) * g.plane + size_t(vb ? yb : 0) * g.pitch + xs;
+      if (t < total_steps) {                               // (b) first: the prefetches do not wait for anything
+        ChainCursor nx = ci;
+        advance(nx);
+        const ChainPiece pn = piece(nx.p);
+        const int reln = nx.j * C::S - 4 * C::P + zr;
+        const bool vna = reln >= 0 && reln < pn.L, vnb = reln >= 0 && reln < pn.Lb;
+        const int xn = C::V * pn.s;
+        // 2 arrays x 2 rows x (V * 4 bytes = up to 4 lines of 128 B, unaligned: 5) = 20 line addresses over 8 threads
+        for (int i = tt; i < 20; i += 8) {
+          const int arr = i & 1, part = (i >> 1) & 1, ln = i >> 2;
+          const bool v = part ? vnb : vna;
+          const int y = pn.ya + reln + (part ? pn.L : 0);
+          int x = xn + 32 * ln;
+          if (x > xn + C::V - 4) x = xn + C::V - 4;
+          if (v && x < g.pitch && !(arr && ut_is_u))
+            prefetch_l2((arr ? utg : ug) + size_t(pn.c) * g.plane + size_t(y) * g.pitch + x);
+        }
+      }
       // all loads of a batch are issued before any is consumed (clamped addresses instead of branches: with a branch
       // per load the compiler serialised eight DRAM round trips per step and this role became the critical path)
       constexpr int QB = (NQ + 1) / 2;
@@ -409,9 +488,8 @@ k_chain_fft(const __grid_constant__ CUtensorMap tm_u, Geom g, State* __restrict_
         float4 ua[QB], ta[QB], ub[QB], tb[QB];
 #pragma unroll
         for (int i = 0; i < QB; ++i) {
-          const int q = q0 + i;
-          const int x4 = 4 * (tt + 8 * q);
-          const bool ok = q < NQ && x4 < C::V && xs + x4 < g.pitch;
+          const int x4 = 4 * (tt + 8 * (q0 + i));
+          const bool ok = (q0 + i) < NQ && x4 < C::V && xs + x4 < g.pitch;
           const int xc = ok ? x4 : 0;
           ua[i] = __ldg(reinterpret_cast<const float4*>(ug + offa + xc));
           ub[i] = __ldg(reinterpret_cast<const float4*>(ug + offb + xc));
@@ -433,18 +511,14 @@ k_chain_fft(const __grid_constant__ CUtensorMap tm_u, Geom g, State* __restrict_
           const bool c0 = ok && Xm < g.Wu, c1 = ok && Xm + 1 < g.Wu, c2 = ok && Xm + 2 < g.Wu, c3 = ok && Xm + 3 < g.Wu;
           da[q] = make_float4(0.5f * (ua[i].x - ta[i].x), 0.5f * (ua[i].y - ta[i].y), 0.5f * (ua[i].z - ta[i].z), 0.5f * (ua[i].w - ta[i].w));
           db[q] = make_float4(0.5f * (ub[i].x - tb[i].x), 0.5f * (ub[i].y - tb[i].y), 0.5f * (ub[i].z - tb[i].z), 0.5f * (ub[i].w - tb[i].w));
-          if (va) {
-            mu = fmaxf(mu, fmaxf(fmaxf(c0 ? ua[i].x : -INFINITY, c1 ? ua[i].y : -INFINITY), fmaxf(c2 ? ua[i].z : -INFINITY, c3 ? ua[i].w : -INFINITY)));
-          }
-          if (vb) {
-            mu = fmaxf(mu, fmaxf(fmaxf(c0 ? ub[i].x : -INFINITY, c1 ? ub[i].y : -INFINITY), fmaxf(c2 ? ub[i].z : -INFINITY, c3 ? ub[i].w : -INFINITY)));
-          }
+          if (va) mu = fmaxf(mu, fmaxf(fmaxf(c0 ? ua[i].x : -INFINITY, c1 ? ua[i].y : -INFINITY), fmaxf(c2 ? ua[i].z : -INFINITY, c3 ? ua[i].w : -INFINITY)));
+          if (vb) mu = fmaxf(mu, fmaxf(fmaxf(c0 ? ub[i].x : -INFINITY, c1 ? ub[i].y : -INFINITY), fmaxf(c2 ? ub[i].z : -INFINITY, c3 ? ub[i].w : -INFINITY)));
         }
       }
     }
     __syncthreads();
     // the TMA stage was consumed by the forward FFT of step t: load step t + 1
-    if (tid == 0 && t + 1 < total_steps) issue(pieces[cf.p], cf.j);
+    if (tid == 0 && t + 1 < total_steps && !(skip & 8)) issue(piece(cf.p), cf.j);
   }
   if (cp.nranks > 1) band_step_max_tail_slot(st, slot, cp, seq, done_counter, reinterpret_cast<int*>(smem));
 }

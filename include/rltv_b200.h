@@ -163,6 +163,8 @@ int rltv_stage_adjoint(rltv_ctx* ctx, float* g_out /* packed HWC (M+MK-1, N+MK-1
  * (pyx:477-491) in one pass from u, psf and the image on the device; also returns the step statistics it reduces,
  * max(u_c) and max|g_c| per channel (pyx:524 with lambda = 1 and ut = u).  RLTV_ERR_STATE if the context does not use it. */
 int rltv_stage_chain(rltv_ctx* ctx, float* g_out /* packed HWC (M+MK-1, N+MK-1, 3) */, float* max6 /* 6 floats or NULL */);
+/* debug: skip roles of the chain kernel (bit 0 forward FFT, 1 MAC, 2 inverse FFT + epilogue, 3 TMA loads); timing only */
+int rltv_debug_chain_roles(int32_t mask);
 /* gk = valid-conv(rot180(u), err) (pyx:567-571).  Direct kernels / MK > 17: uses the residual currently on device
  * (call rltv_stage_residual first).  Row-FFT kernels, MK <= 17: the kernel computes the residual of pyx:557-565
  * itself from u, psf and the image and leaves it on the device (read it with rltv_debug_download_err). */
