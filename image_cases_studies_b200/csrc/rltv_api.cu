@@ -92,6 +92,9 @@ struct rltv_ctx {
   bool chain_ipk_valid = false;
   int inner_count = 0;                  // inner steps enqueued since rltv_begin (statistics slot = parity)
   int inner_in_outer = 0;               // 0 right after ut = u
+  bool ut_is_u = false;                 // adjoint launches of the first inner step read u in place of ut
+  bool fold_psf_step = false;           // PSF_GRAD phase: let the row-FFT finish kernel also do the PSF update + spectra
+  bool psf_step_folded = false;         // ... it did: PSF_STEP has nothing left to launch
   bool use_fft = false;         // forward blur / adjoint through k_conv_fft
   bool use_fft_gradk = false;   // PSF gradient through k_gradk_fft
   bool fuse_residual = false;   // ... which also computes the residual of pyx:557-565 itself (no forward-blur launch)
@@ -248,7 +251,7 @@ int launch_conv_fft_t(rltv_ctx* c, float lambd) {
     ProfScope p(c, ADJ ? F_CONV_ADJ : F_CONV_FWD);
     if (ADJ) {
       if (c->peers.nranks > 1) c->max_seq += 1;
-      k_conv_fft<K, true><<<grid, C::THREADS, SMEM, c->stream>>>(c->tm_err_fft, c->u, c->ut, c->g, c->st, c->wspec,
+      k_conv_fft<K, true><<<grid, C::THREADS, SMEM, c->stream>>>(c->tm_err_fft, c->u, c->ut_is_u ? c->u : c->ut, c->g, c->st, c->wspec,
                                                                lambd, c->gbuf, ntx, nty, y0, y1, c->peers, c->max_seq, c->counters + 1);
     } else {
       k_conv_fft<K, false><<<grid, C::THREADS, SMEM, c->stream>>>(c->tm_u_fft, c->img, c->img, c->g, c->st, c->wspec,
@@ -313,7 +316,7 @@ int launch_conv_t(rltv_ctx* c, float lambd) {
   ProfScope p(c, ADJ ? F_CONV_ADJ : F_CONV_FWD);
   if (ADJ) {
     if (c->peers.nranks > 1) c->max_seq += 1;
-    k_conv<K, true><<<grid, C::THREADS, SMEM, c->stream>>>(c->tm_err_conv, c->tm_u_epi, c->tm_ut_epi, c->g, c->st, c->psf,
+    k_conv<K, true><<<grid, C::THREADS, SMEM, c->stream>>>(c->tm_err_conv, c->tm_u_epi, c->ut_is_u ? c->tm_u_epi : c->tm_ut_epi, c->g, c->st, c->psf,
                                                           lambd, c->gbuf, ntx, nty, y0, y1, c->peers, c->max_seq, c->counters + 1);
   } else {
     k_conv<K, false><<<grid, C::THREADS, SMEM, c->stream>>>(c->tm_u_conv, c->tm_img_epi, c->tm_img_epi, c->g, c->st, c->psf,
@@ -346,8 +349,13 @@ int launch_gradk_fft_t(rltv_ctx* c) {
     }
     {
       ProfScope p(c, F_GRADK);
-      k_gradk_fft_finish<<<3 * K, 512, 0, c->stream>>>(c->st, c->gkf_part, c->gk_nparts, K, c->gk_sum, c->peers, c->gk_seq,
-                                                       c->counters + 2);
+      // whole PSF step in this launch unless the host has to all-reduce the sums in between (NCCL baseline) or a stage
+      // entry point asked for the gradient only
+      const int fold = (c->fold_psf_step && !(c->banded && !c->fused_comm)) ? 1 : 0;
+      c->psf_step_folded = fold != 0;
+      k_gradk_fft_finish<<<3 * K, 512, fold ? 6 * K * K * sizeof(float) : 0, c->stream>>>(
+          c->st, c->gkf_part, c->gk_nparts, K, c->gk_sum, c->peers, c->gk_seq, c->counters + 2, fold, c->params.step_factor,
+          c->params.correlation, c->psf, c->psf_caller, c->wspec);
     }
     return RLTV_OK;
   } else {
@@ -407,8 +415,12 @@ int launch_update(rltv_ctx* c) {
   // chain path: this step's statistics are in slot (inner_count & 1); the update resets the other slot for the next step
   const int slot = c->use_chain ? (c->inner_count & 1) : 0;
   const int reset_slot = c->use_chain ? (slot ^ 1) : -1;
-  k_update<<<grid, 256, 0, c->stream>>>(c->g, c->st, c->u, c->ut, c->gbuf, c->img, c->params.step_factor,
-                                        c->params.lambd, c->params.blind, slot, reset_slot);
+  if (c->inner_in_outer == 0)
+    k_update<true><<<grid, 256, 0, c->stream>>>(c->g, c->st, c->u, nullptr, c->ut, c->gbuf, c->img, c->params.step_factor,
+                                                c->params.lambd, c->params.blind, slot, reset_slot);
+  else
+    k_update<false><<<grid, 256, 0, c->stream>>>(c->g, c->st, c->u, c->ut, nullptr, c->gbuf, c->img, c->params.step_factor,
+                                                 c->params.lambd, c->params.blind, slot, reset_slot);
   return RLTV_OK;
 }
 
@@ -639,12 +651,11 @@ int launch_whiteness(rltv_ctx* c, int advance) {
 int enqueue_phase(rltv_ctx* c, int phase) {
   int rc = RLTV_OK;
   switch (phase) {
-    case RLTV_PH_OUTER_BEGIN: {
-      ProfScope p(c, F_COPY);                                      // ut[:] = u.copy(), pyx:462
-      CU(cudaMemcpyAsync(c->ut, c->u, 3 * c->g.plane * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+    case RLTV_PH_OUTER_BEGIN:
+      // ut[:] = u.copy() (pyx:462) costs nothing here: the first inner step reads u where it would read ut (the
+      // adjoint kernels get u twice, the chain kernel a flag) and its update kernel writes ut <- u_old on the fly
       c->inner_in_outer = 0;
       return RLTV_OK;
-    }
     case RLTV_PH_GRAD:
       if (c->use_chain) {
         if (!c->chain_ipk_valid && (rc = chain_image_spectra(c)) != RLTV_OK) return rc;
@@ -657,8 +668,10 @@ int enqueue_phase(rltv_ctx* c, int phase) {
         return RLTV_OK;
       }
       if ((rc = launch_conv_fwd(c)) != RLTV_OK) return rc;        // pyx:477-488
-      if ((rc = launch_conv_adj(c, c->params.lambd)) != RLTV_OK) return rc;   // pyx:490-491, :519, :524
-      return RLTV_OK;
+      c->ut_is_u = (c->inner_in_outer == 0);
+      rc = launch_conv_adj(c, c->params.lambd);                   // pyx:490-491, :519, :524
+      c->ut_is_u = false;
+      return rc;
     case RLTV_PH_UPDATE:
       if ((rc = launch_update(c)) != RLTV_OK) return rc;          // pyx:527-531, :499-502, :552
       c->inner_count += 1;
@@ -667,8 +680,13 @@ int enqueue_phase(rltv_ctx* c, int phase) {
     case RLTV_PH_PSF_GRAD:
       if (!c->fuse_residual)
         if ((rc = launch_conv_fwd(c)) != RLTV_OK) return rc;      // pyx:557-565 (else inside the PSF-gradient kernel)
-      return launch_gradk(c);                                     // pyx:567-571
+      c->fold_psf_step = true;
+      c->psf_step_folded = false;
+      rc = launch_gradk(c);                                       // pyx:567-571 (+ pyx:574-589 when folded)
+      c->fold_psf_step = false;
+      return rc;
     case RLTV_PH_PSF_STEP:
+      if (c->psf_step_folded) { c->psf_step_folded = false; return RLTV_OK; }
       return launch_psf_update(c);                                // pyx:574-589
     case RLTV_PH_OUTER_END:
       c->outer_since_begin += 1;

@@ -20,8 +20,11 @@ __global__ void k_state_init(State* __restrict__ st) {
 //     DoF = ((g - I)/(g + I))^2 [/lambda if non-blind] ; u = (1-DoF)*u + DoF*I          (pyx:499-502, :552)
 // One float4 per thread per plane row; all five operands share the same (aligned) geometry.
 // ------------------------------------------------------------------------------------------------
+// `first`: first inner step of an outer iteration.  ut == u there (pyx:462 `ut[:] = u.copy()`), so instead of a separate
+// 24 B/px copy pass the update reads u only and WRITES the majoriser: ut <- u_old.  Same bytes as a normal step.
+template <bool FIRST>
 __global__ void __launch_bounds__(256)
-k_update(Geom g, State* __restrict__ st, float* __restrict__ u, const float* __restrict__ ut,
+k_update(Geom g, State* __restrict__ st, float* __restrict__ u, const float* __restrict__ ut, float* __restrict__ ut_out,
          const float* __restrict__ gbuf, const float* __restrict__ img, float step, float lambd, int blind,
          int slot, int reset_slot) {
   if (st->stop) return;
@@ -40,7 +43,7 @@ k_update(Geom g, State* __restrict__ st, float* __restrict__ u, const float* __r
   if (X >= g.Wu) return;
   const size_t off = size_t(c) * g.plane + size_t(Y) * g.pitch + X;
   const float4 uv = *reinterpret_cast<const float4*>(u + off);
-  const float4 tv = *reinterpret_cast<const float4*>(ut + off);
+  const float4 tv = FIRST ? uv : *reinterpret_cast<const float4*>(ut + off);
   const float4 gv = *reinterpret_cast<const float4*>(gbuf + off);
   const float4 iv = *reinterpret_cast<const float4*>(img + off);
   const float uu[4] = {uv.x, uv.y, uv.z, uv.w}, tt[4] = {tv.x, tv.y, tv.z, tv.w};
@@ -61,6 +64,7 @@ k_update(Geom g, State* __restrict__ st, float* __restrict__ u, const float* __r
     o[i] = ((X + i) < g.Wu) ? un : uu[i];
   }
   *reinterpret_cast<float4*>(u + off) = make_float4(o[0], o[1], o[2], o[3]);
+  if (FIRST) *reinterpret_cast<float4*>(ut_out + off) = uv;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -70,10 +74,10 @@ k_update(Geom g, State* __restrict__ st, float* __restrict__ u, const float* __r
 // `psf_caller` reproduces what the CALLER's array holds in the reference: it tracks psf, except that with
 // `correlation` it freezes after the first un-normalised step (pyx:581 writes in place, pyx:585 rebinds).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_psf_update(State* __restrict__ st, const double* __restrict__ gk_sum, int K, float step, int correlation,
-             float* __restrict__ psf, float* __restrict__ psf_caller, Comm* __restrict__ mine, int nranks, int seq) {
-  if (st->stop) return;
+// Body of the PSF step for one whole CTA (any multiple of 32 threads up to 512); `sm` = 6*K*K floats of shared memory.
+__device__ __forceinline__ void psf_update_body(State* __restrict__ st, const double* __restrict__ gk_sum, int K, float step,
+                                                int correlation, float* __restrict__ psf, float* __restrict__ psf_caller,
+                                                Comm* __restrict__ mine, int nranks, int seq, float* __restrict__ sm) {
   const int par = seq & 1;
   if (nranks > 1) {
     // row bands: wait for every band's published PSF-gradient sums of this step (peer stores into `mine`)
@@ -81,11 +85,10 @@ k_psf_update(State* __restrict__ st, const double* __restrict__ gk_sum, int K, f
     __syncthreads();
     __threadfence_system();
   }
-  extern __shared__ float sm[];
   const int KK2 = K * K;
   float* gk = sm;              // [3][KK2]
   float* pk = sm + 3 * KK2;    // [3][KK2]
-  __shared__ float red[8];
+  __shared__ float red[16];
   __shared__ float s_dtp;
   __shared__ double s_sum[3];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -111,7 +114,7 @@ k_psf_update(State* __restrict__ st, const double* __restrict__ gk_sum, int K, f
   mg = warp_max(mg);
   if (lane == 0) red[warp] = mg;
   __syncthreads();
-  if (tid == 0) { float m = 0.f; for (int w = 0; w < 8; ++w) m = fmaxf(m, red[w]); s_dtp = m; }
+  if (tid == 0) { float m = 0.f; for (int w = 0; w < int(blockDim.x >> 5); ++w) m = fmaxf(m, red[w]); s_dtp = m; }
   __syncthreads();
   const float amax_gk = s_dtp;
   __syncthreads();
@@ -119,7 +122,7 @@ k_psf_update(State* __restrict__ st, const double* __restrict__ gk_sum, int K, f
   if (lane == 0) red[warp] = mp;
   __syncthreads();
   if (tid == 0) {
-    float m = -INFINITY; for (int w = 0; w < 8; ++w) m = fmaxf(m, red[w]);
+    float m = -INFINITY; for (int w = 0; w < int(blockDim.x >> 5); ++w) m = fmaxf(m, red[w]);
     const float dtp = (step / float(K)) * m / (amax_gk + 1e-15f);      // pyx:574
     s_dtp = dtp;
     st->dtpsf = dtp;
@@ -159,6 +162,14 @@ k_psf_update(State* __restrict__ st, const double* __restrict__ gk_sum, int K, f
     if (!correlation) psf_caller[i] = v;
   }
   if (tid == 0) st->blind_steps += 1;
+}
+
+__global__ void __launch_bounds__(256)
+k_psf_update(State* __restrict__ st, const double* __restrict__ gk_sum, int K, float step, int correlation,
+             float* __restrict__ psf, float* __restrict__ psf_caller, Comm* __restrict__ mine, int nranks, int seq) {
+  if (st->stop) return;
+  extern __shared__ float sm[];
+  psf_update_body(st, gk_sum, K, step, correlation, psf, psf_caller, mine, nranks, seq, sm);
 }
 
 // normalize_kernel (pyx:73-75): same clip + normalise on a planar [3][K*K] buffer, one block.

@@ -18,6 +18,7 @@
 #pragma once
 #include "rltv_band.cuh"
 #include "rltv_common.cuh"
+#include "rltv_elementwise.cuh"
 #include "rltv_fft.cuh"
 #include "rltv_stencil.cuh"
 #include "rltv_tma.cuh"
@@ -578,10 +579,16 @@ k_gradk_fft(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
 // Finish of the PSF gradient, one CTA per (channel, dy) row of frequency-domain sums, everything in double and in a
 // fixed order (deterministic):  sum the per-CTA partials -> untangle A[k] = (C[k] + conj(C[-k]))/2 (two real rows were
 // packed per complex FFT) -> K-lag inverse DFT -> gk_sum.  With row bands the last CTA raises the "published" flags.
+// FOLD (single launch for the whole PSF step): the last CTA to finish also runs the PSF update (pyx:574-589, waiting for
+// the other bands' sums first when the frame is sharded) and refreshes the tap spectra of the new PSF -- two single-CTA
+// launches and their launch gaps less per inner step.
 __global__ void __launch_bounds__(512)
-k_gradk_fft_finish(const State* __restrict__ st, const float2* __restrict__ part, int nparts, int K,
-                   double* __restrict__ gk_sum, CommPeers cp, int seq, unsigned* __restrict__ ticket) {
+k_gradk_fft_finish(State* __restrict__ st, const float2* __restrict__ part, int nparts, int K,
+                   double* __restrict__ gk_sum, CommPeers cp, int seq, unsigned* __restrict__ ticket,
+                   int fold, float step, int correlation, float* __restrict__ psf, float* __restrict__ psf_caller,
+                   float2* __restrict__ wspec) {
   if (st->stop) return;
+  extern __shared__ float sm_psf[];
   __shared__ double2 sh[4][FFT_N];
   __shared__ double2 A[FFT_N];
   __shared__ double2 tw64[FFT_N];
@@ -641,14 +648,42 @@ k_gradk_fft_finish(const State* __restrict__ st, const float2* __restrict__ part
     if (cp.nranks > 1)
       for (int rr = 0; rr < cp.nranks; ++rr) cp.peer[rr]->gk_val[par][cp.rank][o] = sum;
   }
-  if (cp.nranks > 1) {
+  if (cp.nranks > 1 || fold) {
+    __shared__ int s_last;
     __threadfence_system();
     __syncthreads();
-    if (tid == 0 && atomicAdd(ticket, 1u) == gridDim.x - 1) {
-      *ticket = 0u;
-      __threadfence_system();
-      for (int rr = 0; rr < cp.nranks; ++rr) *reinterpret_cast<volatile int*>(&cp.peer[rr]->gk_flag[par][cp.rank]) = seq;
-      __threadfence_system();
+    if (tid == 0) {
+      const int last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+      if (last) {
+        *ticket = 0u;
+        __threadfence_system();
+        if (cp.nranks > 1) {
+          for (int rr = 0; rr < cp.nranks; ++rr) *reinterpret_cast<volatile int*>(&cp.peer[rr]->gk_flag[par][cp.rank]) = seq;
+          __threadfence_system();
+        }
+      }
+      s_last = last;
+    }
+    __syncthreads();
+    if (fold && s_last) {
+      psf_update_body(st, gk_sum, K, step, correlation, psf, psf_caller, cp.peer[cp.rank], cp.nranks, seq, sm_psf);
+      float2* twf = reinterpret_cast<float2*>(sh);     // the partial-sum scratch is free now
+      if (tid < FFT_N) twf[tid] = make_float2(float(tw64[tid].x), float(tw64[tid].y));
+      __syncthreads();
+      // tap spectra of the new PSF (same definition as k_psf_spectrum), twiddles from the table built above
+      const int n_out = 2 * 3 * K * FFT_N;
+      for (int o = tid; o < n_out; o += blockDim.x) {
+        const int kb = o & (FFT_N - 1), r = o >> 7, ky = r % K, c = (r / K) % 3, dir = r / (3 * K);
+        float re = 0.f, im = 0.f;                       // float like k_psf_spectrum (B200's FP64 rate would make this the
+        for (int kx = 0; kx < K; ++kx) {                // longest part of the PSF step)
+          const int src = dir ? (ky * K + kx) : ((K - 1 - ky) * K + (K - 1 - kx));
+          const float w = psf[size_t(c) * K * K + src];
+          const float2 e = twf[((kx - P) * kb) & (FFT_N - 1)];
+          re = fmaf(w, e.x, re);
+          im = fmaf(w, e.y, im);
+        }
+        wspec[o] = make_float2(re * (1.f / FFT_N), im * (1.f / FFT_N));
+      }
     }
   }
 }
