@@ -73,6 +73,10 @@ SYMBOLS = [
     ("rltv_set_rank", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
     ("rltv_ipc_attach", C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32]),
     ("rltv_set_whiteness_owner", C.c_int, [C.c_void_p, C.c_int32]),
+    ("rltv_gather_alloc", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("rltv_gather_attach", C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    ("rltv_gather_push", C.c_int, [C.c_void_p, C.c_uint32]),
+    ("rltv_gather_download", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     ("rltv_enqueue_phase", C.c_int, [C.c_void_p, C.c_int32]),
     ("rltv_device_ptr", C.c_void_p, [C.c_void_p, C.c_char_p, C.POINTER(C.c_size_t)]),
     ("rltv_poll_record", C.c_int, [C.c_void_p, C.c_int32]),

@@ -92,6 +92,9 @@ struct rltv_ctx {
   bool chain_ipk_valid = false;
   int inner_count = 0;                  // inner steps enqueued since rltv_begin (statistics slot = parity)
   int inner_in_outer = 0;               // 0 right after ut = u
+  float* gather_stage = nullptr;        // full-frame HWC staging buffer of THIS rank (device), IPC-exported
+  float* gather_peer[MAXR] = {};        // other ranks' staging buffers (IPC-mapped)
+  void* gather_peer_base[MAXR] = {};
   bool ut_is_u = false;                 // adjoint launches of the first inner step read u in place of ut
   bool fold_psf_step = false;           // PSF_GRAD phase: let the row-FFT finish kernel also do the PSF update + spectra
   bool psf_step_folded = false;         // ... it did: PSF_STEP has nothing left to launch
@@ -105,8 +108,10 @@ struct rltv_ctx {
   void* peer_base[MAXR] = {};
   CommPeers peers{};            // peers.nranks == 1: whole frame or NCCL-baseline mode (no in-kernel exchange)
   int rank = 0, world = 1;
+  int world_rank = 0;           // rank in the process group even when the kernels run with rank 0 (NCCL baseline)
   bool fused_comm = false;      // true: in-kernel all-gathers over NVLink; false: host all-reduces (NCCL baseline)
-  unsigned* counters = nullptr; // [0] halo push, [1] adjoint, [2] gradk "last CTA" tickets
+  unsigned* counters = nullptr; // "last CTA" tickets: [0] k_halo_push (unused since the update pushes), [1] adjoint / chain,
+                                // [2] gradk, [3] whiteness, [4..6] k_update halo exchange (top side, bottom side, grid)
   int halo_seq = 0;             // exchange numbers: identical on every band, never reset
   int max_seq = 0, gk_seq = 0, stop_seq = 0;
   bool white_owner = true;
@@ -415,12 +420,24 @@ int launch_update(rltv_ctx* c) {
   // chain path: this step's statistics are in slot (inner_count & 1); the update resets the other slot for the next step
   const int slot = c->use_chain ? (c->inner_count & 1) : 0;
   const int reset_slot = c->use_chain ? (slot ^ 1) : -1;
+  HaloPush hp{};
+  if (c->side[0].peer_u || c->side[1].peer_u) {            // row band with at least one neighbour: push inside the update
+    c->halo_seq += 1;
+    const int* flags = reinterpret_cast<const Comm*>(reinterpret_cast<const char*>(c->u) + c->flag_offset)->halo_flag;
+    hp.top = c->side[0];
+    hp.bot = c->side[1];
+    hp.counters = c->counters + 4;
+    hp.flag_from_top = c->side[0].peer_u ? flags + 0 : nullptr;
+    hp.flag_from_bot = c->side[1].peer_u ? flags + 1 : nullptr;
+    hp.seq = c->halo_seq;
+    hp.enabled = 1;
+  }
   if (c->inner_in_outer == 0)
     k_update<true><<<grid, 256, 0, c->stream>>>(c->g, c->st, c->u, nullptr, c->ut, c->gbuf, c->img, c->params.step_factor,
-                                                c->params.lambd, c->params.blind, slot, reset_slot);
+                                                c->params.lambd, c->params.blind, slot, reset_slot, hp);
   else
     k_update<false><<<grid, 256, 0, c->stream>>>(c->g, c->st, c->u, c->ut, nullptr, c->gbuf, c->img, c->params.step_factor,
-                                                 c->params.lambd, c->params.blind, slot, reset_slot);
+                                                 c->params.lambd, c->params.blind, slot, reset_slot, hp);
   return RLTV_OK;
 }
 
@@ -541,16 +558,6 @@ int launch_psf_update(rltv_ctx* c) {
                                                                   c->peers.peer[c->rank], c->peers.nranks, c->gk_seq);
   }
   return launch_psf_spectrum(c);
-}
-
-int launch_halo_push(rltv_ctx* c) {
-  if (!c->side[0].peer_u && !c->side[1].peer_u) return RLTV_OK;
-  c->halo_seq += 1;
-  const int* flags = reinterpret_cast<const Comm*>(reinterpret_cast<const char*>(c->u) + c->flag_offset)->halo_flag;
-  ProfScope p(c, F_HALO);
-  k_halo_push<<<2 * c->num_sms, 256, 0, c->stream>>>(c->g, c->st, c->u, c->side[0], c->side[1], c->counters + 0, c->halo_seq,
-                                                     c->side[0].peer_u ? flags + 0 : nullptr, c->side[1].peer_u ? flags + 1 : nullptr);
-  return RLTV_OK;
 }
 
 int next_pow2(int v) {
@@ -676,7 +683,7 @@ int enqueue_phase(rltv_ctx* c, int phase) {
       if ((rc = launch_update(c)) != RLTV_OK) return rc;          // pyx:527-531, :499-502, :552
       c->inner_count += 1;
       c->inner_in_outer += 1;
-      return launch_halo_push(c);
+      return RLTV_OK;                                             // (row bands: the halo exchange happened inside k_update)
     case RLTV_PH_PSF_GRAD:
       if (!c->fuse_residual)
         if ((rc = launch_conv_fwd(c)) != RLTV_OK) return rc;      // pyx:557-565 (else inside the PSF-gradient kernel)
@@ -825,8 +832,8 @@ int rltv_create_band(rltv_ctx** out, int32_t device, int32_t M, int32_t N, int32
   CU(cudaMalloc(&c->psf_hwc, kb));
   CU(cudaMalloc(&c->st, sizeof(State)));
   CU(cudaMemsetAsync(c->st, 0, sizeof(State), c->stream));
-  CU(cudaMalloc(&c->counters, 4 * sizeof(unsigned)));
-  CU(cudaMemsetAsync(c->counters, 0, 4 * sizeof(unsigned), c->stream));
+  CU(cudaMalloc(&c->counters, 8 * sizeof(unsigned)));
+  CU(cudaMemsetAsync(c->counters, 0, 8 * sizeof(unsigned), c->stream));
   c->peers.nranks = 1;
   c->peers.rank = 0;
   c->peers.peer[0] = reinterpret_cast<Comm*>(reinterpret_cast<char*>(c->u) + c->flag_offset);
@@ -882,6 +889,8 @@ int rltv_destroy(rltv_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   for (auto& pb : c->peer_base) if (pb) cudaIpcCloseMemHandle(pb);
+  for (auto& pb : c->gather_peer_base) if (pb) cudaIpcCloseMemHandle(pb);
+  cudaFree(c->gather_stage);
   float* f[] = {c->u, c->ut, c->gbuf, c->img, c->err, c->staging, c->psf, c->psf_caller, c->psf_hwc,
                 c->gk_partial, c->rowmin, c->rowmax, c->mr_out};
   for (auto p : f) cudaFree(p);
@@ -1102,6 +1111,7 @@ int rltv_set_rank(rltv_ctx* c, int32_t rank, int32_t world, int32_t fused) {
   if (!c) return fail(RLTV_ERR_ARG, "null context");
   if (world < 1 || world > MAXR || rank < 0 || rank >= world) return fail(RLTV_ERR_ARG, "bad rank/world (at most 8 bands)");
   c->rank = rank;
+  c->world_rank = rank;
   c->world = world;
   c->fused_comm = fused != 0;
   Comm* mine = reinterpret_cast<Comm*>(reinterpret_cast<char*>(c->u) + c->flag_offset);
@@ -1152,6 +1162,66 @@ int rltv_ipc_attach(rltv_ctx* c, int32_t peer_rank, const void* handle64, int32_
   }
   if (s.src_row < c->g.own0 || s.src_row + s.nrows > c->g.own1 || s.dst_row < 0 || s.dst_row + s.nrows > peer_row_hi - peer_row_lo)
     return fail(RLTV_ERR_ARG, "halo rows do not fit: every band must own at least 2*(MK/2) rows");
+  return RLTV_OK;
+}
+
+// ---- device-side gather of the result bands ------------------------------------------------------------
+int rltv_gather_alloc(rltv_ctx* c, void* handle64_out) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  const Geom& g = c->g;
+  const size_t HuG = size_t(g.M) + g.K - 1;
+  if (!c->gather_stage) CU(cudaMalloc(&c->gather_stage, HuG * g.Wu * 3 * sizeof(float)));
+  if (handle64_out) {
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, c->gather_stage));
+    std::memcpy(handle64_out, &h, 64);
+  }
+  return RLTV_OK;
+}
+
+int rltv_gather_attach(rltv_ctx* c, int32_t peer_rank, const void* handle64) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  if (peer_rank < 0 || peer_rank >= MAXR || !handle64) return fail(RLTV_ERR_ARG, "bad peer rank/handle");
+  if (c->gather_peer_base[peer_rank]) return RLTV_OK;
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle64, 64);
+  void* base = nullptr;
+  CU(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+  c->gather_peer_base[peer_rank] = base;
+  c->gather_peer[peer_rank] = reinterpret_cast<float*>(base);
+  return RLTV_OK;
+}
+
+int rltv_gather_push(rltv_ctx* c, uint32_t dst_rank_mask) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  const Geom& g = c->g;
+  const int nrows = c->own_hi - c->own_lo;
+  for (int r = 0; r < MAXR; ++r) {
+    if (!(dst_rank_mask & (1u << r))) continue;
+    float* dst = (r == c->world_rank) ? c->gather_stage : c->gather_peer[r];
+    if (!dst) return fail(RLTV_ERR_STATE, "gather buffer of the destination rank is not allocated / attached");
+    // owned rows, planar -> packed HWC rows of the FULL frame at frame row own_lo
+    k_planar_to_hwc<<<dim3(hwc_grid(g.Wu), nrows), 256, 0, c->stream>>>(c->u, g, g.own0, 0, nrows, g.Wu,
+                                                                       dst + size_t(c->own_lo) * g.Wu * 3, size_t(g.Wu) * 3);
+    c->launches++;
+  }
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(c->stream));          // the caller's barrier may follow immediately
+  return RLTV_OK;
+}
+
+int rltv_gather_download(rltv_ctx* c, float* u, size_t u_rs) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  const Geom& g = c->g;
+  if (!c->gather_stage || !u) return fail(RLTV_ERR_STATE, "no gather buffer / destination");
+  if (u_rs < size_t(g.Wu) * 12) return fail(RLTV_ERR_ARG, "u row stride smaller than a packed row");
+  const size_t HuG = size_t(g.M) + g.K - 1;
+  CU(cudaMemcpy2DAsync(u, u_rs, c->gather_stage, size_t(g.Wu) * 12, size_t(g.Wu) * 12, HuG, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
   return RLTV_OK;
 }
 

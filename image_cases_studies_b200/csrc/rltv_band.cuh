@@ -2,9 +2,9 @@
 // kernels themselves with peer stores over NVLink into IPC-mapped memory of the other bands, ordered by
 // step-numbered flags -- no host involvement and no NCCL inside an outer iteration:
 //
-//   halo exchange   after the update kernel rewrote the owned rows of u (lib/deconvolution.pyx:527-531, :552)
-//                   each band pushes its first / last 2P owned rows into the bottom / top halo of its
-//                   neighbours (k_halo_push) and the same kernel ends only when the neighbours' rows have landed;
+//   halo exchange   the update kernel itself (k_update, rltv_elementwise.cuh) stores the first / last 2P owned rows it
+//                   rewrites (lib/deconvolution.pyx:527-531, :552) into the bottom / top halo of the neighbours as
+//                   well, and ends only when the neighbours' rows have landed here;
 //   step scalars    the last CTA of the adjoint kernel publishes the band's max(u_c), max|G_c| (pyx:524) into slot
 //                   [rank] of EVERY band's Comm block, then waits for all slots and takes the max;
 //   PSF gradient    the last CTA of k_gradk / k_gradk_fft_finish sums the per-CTA partials (double, fixed order) and publishes the
@@ -53,45 +53,6 @@ __device__ __forceinline__ void spin_until(const int* flag, int seq) {
   const long long t0 = clock64();
   while (*reinterpret_cast<const volatile int*>(flag) < seq) {
     if (clock64() - t0 > 20000000000LL) __trap();   // a lost peer faults the launch (~10 s) instead of hanging
-  }
-}
-
-// grid-stride float4 copy of nrows x pitch x 3 planes to each neighbour, then (last CTA) raise the flags.
-__global__ void __launch_bounds__(256)
-k_halo_push(Geom g, const State* __restrict__ st, const float* __restrict__ u, HaloSide top, HaloSide bot,
-            unsigned* __restrict__ done_counter, int seq, const int* flag_from_top, const int* flag_from_bot) {
-  if (st->stop) return;
-  const int row4 = g.pitch / 4;
-  const HaloSide sides[2] = {top, bot};
-#pragma unroll
-  for (int sd = 0; sd < 2; ++sd) {
-    const HaloSide& h = sides[sd];
-    if (!h.peer_u) continue;
-    const int per_plane = h.nrows * row4;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 3 * per_plane; i += gridDim.x * blockDim.x) {
-      const int c = i / per_plane, r = i - c * per_plane;
-      const float4 v = reinterpret_cast<const float4*>(u + size_t(c) * g.plane + size_t(h.src_row) * g.pitch)[r];
-      reinterpret_cast<float4*>(h.peer_u + size_t(c) * h.peer_plane + size_t(h.dst_row) * g.pitch)[r] = v;
-    }
-  }
-  __threadfence_system();          // peer stores of this thread are visible system-wide before the flag
-  __syncthreads();
-  __shared__ bool last;
-  if (threadIdx.x == 0) last = (atomicAdd(done_counter, 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (last && threadIdx.x == 0) {
-    *done_counter = 0u;
-    __threadfence_system();
-    if (top.peer_u) *reinterpret_cast<volatile int*>(top.peer_flag) = seq;
-    if (bot.peer_u) *reinterpret_cast<volatile int*>(bot.peer_flag) = seq;
-    __threadfence_system();
-  }
-  // ... and the kernel does not end before the neighbours' pushes number `seq` have landed in this band's halo rows:
-  // the next reader of u simply follows in stream order.  (A neighbour's push never waits for this kernel.)
-  if (last && threadIdx.x < 2) {
-    const int* f = threadIdx.x == 0 ? flag_from_top : flag_from_bot;
-    if (f) spin_until(f, seq);
-    __threadfence_system();
   }
 }
 

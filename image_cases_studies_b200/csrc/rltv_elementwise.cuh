@@ -22,11 +22,25 @@ __global__ void k_state_init(State* __restrict__ st) {
 // ------------------------------------------------------------------------------------------------
 // `first`: first inner step of an outer iteration.  ut == u there (pyx:462 `ut[:] = u.copy()`), so instead of a separate
 // 24 B/px copy pass the update reads u only and WRITES the majoriser: ut <- u_old.  Same bytes as a normal step.
+// Row bands: the update kernel also does the halo exchange.  Threads that rewrite one of the first / last 2P owned rows
+// store the new values straight into the neighbour's halo rows as well (peer stores over NVLink); the CTA that completes
+// a side raises the neighbour's step-numbered flag; and the last CTA of the grid waits for the NEIGHBOURS' flags, so
+// that when this kernel ends the band's own halo rows are up to date for whatever reads u next.  (Round 1 did this in a
+// separate copy kernel, k_halo_push: 22 us per inner step that did not shrink with the band.)
+struct HaloPush {
+  HaloSide top, bot;
+  unsigned* counters;          // [0] top side, [1] bottom side, [2] whole grid
+  const int* flag_from_top;    // raised by the band above when ITS rows have landed here (nullptr: no neighbour)
+  const int* flag_from_bot;
+  int seq;
+  int enabled;
+};
+
 template <bool FIRST>
 __global__ void __launch_bounds__(256)
 k_update(Geom g, State* __restrict__ st, float* __restrict__ u, const float* __restrict__ ut, float* __restrict__ ut_out,
          const float* __restrict__ gbuf, const float* __restrict__ img, float step, float lambd, int blind,
-         int slot, int reset_slot) {
+         int slot, int reset_slot, HaloPush hp) {
   if (st->stop) return;
   const int c = blockIdx.z;
   const int Y = g.own0 + blockIdx.y;          // only owned rows are updated; halo rows arrive from the neighbours
@@ -40,8 +54,9 @@ k_update(Geom g, State* __restrict__ st, float* __restrict__ u, const float* __r
       st->smax[reset_slot][3 + c] = 0;
     }
   }
-  if (X >= g.Wu) return;
-  const size_t off = size_t(c) * g.plane + size_t(Y) * g.pitch + X;
+  if (X >= g.Wu && !hp.enabled) return;
+  const bool active = X < g.Wu;
+  const size_t off = size_t(c) * g.plane + size_t(Y) * g.pitch + (active ? X : 0);
   const float4 uv = *reinterpret_cast<const float4*>(u + off);
   const float4 tv = FIRST ? uv : *reinterpret_cast<const float4*>(ut + off);
   const float4 gv = *reinterpret_cast<const float4*>(gbuf + off);
@@ -63,8 +78,40 @@ k_update(Geom g, State* __restrict__ st, float* __restrict__ u, const float* __r
     }
     o[i] = ((X + i) < g.Wu) ? un : uu[i];
   }
-  *reinterpret_cast<float4*>(u + off) = make_float4(o[0], o[1], o[2], o[3]);
-  if (FIRST) *reinterpret_cast<float4*>(ut_out + off) = uv;
+  if (active) {
+    *reinterpret_cast<float4*>(u + off) = make_float4(o[0], o[1], o[2], o[3]);
+    if (FIRST) *reinterpret_cast<float4*>(ut_out + off) = uv;
+  }
+  if (hp.enabled) {
+    const bool te = hp.top.peer_u && Y >= hp.top.src_row && Y < hp.top.src_row + hp.top.nrows;     // CTA-uniform
+    const bool be = hp.bot.peer_u && Y >= hp.bot.src_row && Y < hp.bot.src_row + hp.bot.nrows;
+    if (active && te)
+      *reinterpret_cast<float4*>(hp.top.peer_u + size_t(c) * hp.top.peer_plane + size_t(hp.top.dst_row + Y - hp.top.src_row) * g.pitch + X) =
+          make_float4(o[0], o[1], o[2], o[3]);
+    if (active && be)
+      *reinterpret_cast<float4*>(hp.bot.peer_u + size_t(c) * hp.bot.peer_plane + size_t(hp.bot.dst_row + Y - hp.bot.src_row) * g.pitch + X) =
+          make_float4(o[0], o[1], o[2], o[3]);
+    __threadfence_system();          // this thread's peer stores are visible system-wide before any flag
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (te && atomicAdd(hp.counters + 0, 1u) == unsigned(gridDim.x * hp.top.nrows * 3 - 1)) {
+        hp.counters[0] = 0u;
+        __threadfence_system();
+        *reinterpret_cast<volatile int*>(hp.top.peer_flag) = hp.seq;
+      }
+      if (be && atomicAdd(hp.counters + 1, 1u) == unsigned(gridDim.x * hp.bot.nrows * 3 - 1)) {
+        hp.counters[1] = 0u;
+        __threadfence_system();
+        *reinterpret_cast<volatile int*>(hp.bot.peer_flag) = hp.seq;
+      }
+      if (atomicAdd(hp.counters + 2, 1u) == gridDim.x * gridDim.y * gridDim.z - 1) {
+        hp.counters[2] = 0u;
+        if (hp.flag_from_top) spin_until(hp.flag_from_top, hp.seq);
+        if (hp.flag_from_bot) spin_until(hp.flag_from_bot, hp.seq);
+        __threadfence_system();
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -147,13 +147,21 @@ class BandSolver:
         psf = np.ascontiguousarray(psf, dtype=np.float32)
         nat.check(nat.lib.rltv_upload_band(self._ctx, nat.ptr(img), img.strides[0], i0, i1 - i0, nat.ptr(ub),
                                            ub.strides[0], nat.ptr(psf)))
-        self.dist.barrier(group=self.group)          # halos on every rank come from the same host frame
+        # No barrier here with comm="fused": the first peer store into a neighbour's halo happens in the first update
+        # kernel, which follows the first gradient kernel, whose tail waits for the step statistics of EVERY band --
+        # i.e. for every band's first kernel, which its own upload precedes in stream order.
+        if not self.fused:
+            self.dist.barrier(group=self.group)
 
     def download(self, u, psf_caller=None, psf_refined=None, gather="all"):
         """Writes this band's owned rows into ``u``.  gather="all": every rank ends up with the full frame (the SPMD
         drop-in contract); "root": only rank 0 does (the other ranks keep their own band); False/None: no exchange."""
         torch, dist = self.torch, self.dist
+        if gather is True:
+            gather = "all"
         own_lo, own_hi = self.band[2], self.band[3]
+        if gather and self.world > 1 and (gather == "all" or self.rank == 0):
+            own_hi = own_lo                          # this rank receives the whole frame through the device gather below
         rows = u[own_lo:own_hi]
         tmp = rows if (_rows_ok(rows) and rows.flags.writeable) else np.empty(rows.shape, np.float32)
         pc = psf_caller if psf_caller is None or psf_caller.flags.c_contiguous else np.empty_like(psf_caller, order="C")
@@ -167,29 +175,42 @@ class BandSolver:
             psf_caller[...] = pc
         if psf_refined is not None and pr is not psf_refined:
             psf_refined[...] = pr
-        if gather is True:
-            gather = "all"
         if gather and self.world > 1:
-            dev = f"cuda:{self.device}"
-            grank = (lambda r: dist.get_global_rank(self.group, r)) if self.group is not None else (lambda r: r)
-            if gather == "all":
-                for r, b in enumerate(self.bands):
-                    t = torch.empty((b[3] - b[2], u.shape[1], 3), dtype=torch.float32, device=dev)
-                    if r == self.rank:
-                        t.copy_(torch.from_numpy(np.ascontiguousarray(u[b[2]:b[3]])))
-                    dist.broadcast(t, src=grank(r), group=self.group)
-                    if r != self.rank:
-                        u[b[2]:b[3]] = t.cpu().numpy()
-            else:                                    # root: bands travel to rank 0 only (NCCL point to point)
-                if self.rank == 0:
-                    for r, b in enumerate(self.bands[1:], start=1):
-                        t = torch.empty((b[3] - b[2], u.shape[1], 3), dtype=torch.float32, device=dev)
-                        dist.recv(t, src=grank(r), group=self.group)
-                        u[b[2]:b[3]] = t.cpu().numpy()
-                else:
-                    b = self.band
-                    t = torch.from_numpy(np.ascontiguousarray(u[b[2]:b[3]])).to(dev)
-                    dist.send(t, dst=grank(0), group=self.group)
+            self._gather_on_device(u, gather)
+        return u
+
+    def _gather_on_device(self, u, gather):
+        """Result bands travel GPU to GPU: every band converts its owned rows planar -> HWC straight into the full-frame
+        staging buffer of the destination rank(s) (peer stores over NVLink into CUDA-IPC-mapped memory), then each
+        destination copies the whole frame to its host array in ONE transfer.  (Round 1 bounced every band through the
+        host twice and through NCCL send/recv: ~145 ms of a 305 ms call at 8 GPUs.)"""
+        dist = self.dist
+        dests = list(range(self.world)) if gather == "all" else [0]
+        key = tuple(dests)
+        if getattr(self, "_gather_ready", None) != key:
+            h = (C.c_char * 64)()
+            mine = self.rank in dests
+            if mine:
+                nat.check(nat.lib.rltv_gather_alloc(self._ctx, h))
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(h.raw) if mine else None, group=self.group)
+            for r in dests:
+                if r != self.rank:
+                    hb = (C.c_char * 64).from_buffer_copy(handles[r])
+                    nat.check(nat.lib.rltv_gather_attach(self._ctx, r, hb))
+            self._gather_ready = key
+        mask = 0
+        for r in dests:
+            mask |= 1 << r
+        nat.check(nat.lib.rltv_gather_push(self._ctx, mask))       # synchronises this rank's stream
+        dist.barrier(group=self.group)                             # every band has landed in every destination
+        if self.rank in dests:
+            if _rows_ok(u) and u.flags.writeable:
+                nat.check(nat.lib.rltv_gather_download(self._ctx, nat.ptr(u), u.strides[0]))
+            else:
+                tmp = np.empty(u.shape, np.float32)
+                nat.check(nat.lib.rltv_gather_download(self._ctx, nat.ptr(tmp), tmp.strides[0]))
+                u[...] = tmp
         return u
 
     # -- stepping ------------------------------------------------------------------------------------------

@@ -154,6 +154,16 @@ void* rltv_device_ptr(rltv_ctx* ctx, const char* name, size_t* nbytes);
 int rltv_poll_record(rltv_ctx* ctx, int32_t it);
 int rltv_poll_wait(rltv_ctx* ctx, int32_t it, int32_t* stop);
 
+/* ---- gathering the result bands on the device ----------------------------------------------------------------
+ * The destination rank allocates a full-frame HWC staging buffer (rltv_gather_alloc) and exports it over CUDA IPC;
+ * every band converts its OWNED rows planar -> HWC straight into the mapped buffer(s) (peer stores over NVLink,
+ * rltv_gather_push), and after a barrier of the caller's choice the destination copies the whole frame to the host in
+ * one transfer (rltv_gather_download).  Replaces a host round trip per band (download, re-upload, NCCL send/recv). */
+int rltv_gather_alloc(rltv_ctx* ctx, void* handle64_out);
+int rltv_gather_attach(rltv_ctx* ctx, int32_t peer_rank, const void* handle64);
+int rltv_gather_push(rltv_ctx* ctx, uint32_t dst_rank_mask /* bit r: band r's staging buffer (own rank: the local one) */);
+int rltv_gather_download(rltv_ctx* ctx, float* u, size_t u_row_stride_bytes);
+
 /* ---- stage-level entry points (parity tests drive each kernel against the oracle) ------------------ */
 /* out[M][N][3] = valid-conv(u, psf) - image   (pyx:477-488) */
 int rltv_stage_residual(rltv_ctx* ctx, float* err_out /* packed HWC (M,N,3) */);

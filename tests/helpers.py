@@ -37,3 +37,25 @@ def load_golden(name):
     for k in ("blind", "correlation"):
         d[k] = bool(d[k])
     return d
+
+
+def smooth_case(M, N, K, blind, seed, box=5):
+    """Box-smoothed scene + a little noise: the non-blind whiteness statistic turns around after ~20
+    outer iterations, so the reference's stop rule (lib/deconvolution.pyx:643-654) fires.
+    Returns (image, u0, psf0, window) as the golden-vector generator and the row-band worker use them."""
+    from image_cases_studies_b200 import synthetic
+    from image_cases_studies_b200.lib import utils
+    rng = np.random.default_rng(seed)
+    p = K // 2
+    s = 0.1 + 0.8 * rng.random((M + 2 * p, N + 2 * p, 3), dtype=np.float32)
+    # separable box filter in plain numpy (no scipy.ndimage dependency)
+    ker = np.ones(box) / box
+    for ax in (0, 1):
+        s = np.apply_along_axis(lambda v: np.convolve(np.pad(v, box // 2, mode="reflect"), ker, mode="valid"), ax, s)
+    s = s.astype(np.float32)
+    kt = utils.stack3(utils.gaussian_kernel(K, K / 4))
+    image = synthetic._valid_conv_fft(s, kt)
+    image += (0.002 * rng.standard_normal(image.shape)).astype(np.float32)
+    u0 = np.ascontiguousarray(np.pad(image, ((p, p), (p, p), (0, 0)), mode="edge"))
+    psf0 = utils.stack3(utils.uniform_kernel(K)) if blind else kt
+    return image, u0, psf0, synthetic.default_window(M, N, p)
