@@ -18,12 +18,13 @@ LIB_PATH = Path(os.environ["RLTV_LIB"]) if os.environ.get("RLTV_LIB") else PKG /
 RLTV_MAX_HISTORY = 4096
 RLTV_MAX_MK = 31
 INNER_ITER = 5
+MODE_MM, MODE_MM_TV = 0, 1
 
 
 class Params(C.Structure):
     _fields_ = [("top", C.c_int32), ("bottom", C.c_int32), ("left", C.c_int32), ("right", C.c_int32),
                 ("tau", C.c_float), ("iterations", C.c_int32), ("step_factor", C.c_float), ("lambd", C.c_float),
-                ("blind", C.c_int32), ("correlation", C.c_int32)]
+                ("blind", C.c_int32), ("correlation", C.c_int32), ("mode", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -73,6 +74,7 @@ SYMBOLS = [
     ("rltv_set_rank", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
     ("rltv_ipc_attach", C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32]),
     ("rltv_set_whiteness_owner", C.c_int, [C.c_void_p, C.c_int32]),
+    ("rltv_download_image", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     ("rltv_gather_alloc", C.c_int, [C.c_void_p, C.c_void_p]),
     ("rltv_gather_attach", C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     ("rltv_gather_push", C.c_int, [C.c_void_p, C.c_uint32]),

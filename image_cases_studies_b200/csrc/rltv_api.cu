@@ -30,6 +30,7 @@
 #include "rltv_stencil.cuh"
 #include "rltv_stencil_fft.cuh"
 #include "rltv_tv.cuh"
+#include "rltv_tvmode.cuh"
 #include "rltv_whiteness.cuh"
 
 using namespace rltv;
@@ -92,6 +93,7 @@ struct rltv_ctx {
   bool chain_ipk_valid = false;
   int inner_count = 0;                  // inner steps enqueued since rltv_begin (statistics slot = parity)
   int inner_in_outer = 0;               // 0 right after ut = u
+  float *tvut1 = nullptr, *tvut2 = nullptr, *tbuf = nullptr;   // TV-alive mode: TV(ut) maps, T = TV gradient term
   float* gather_stage = nullptr;        // full-frame HWC staging buffer of THIS rank (device), IPC-exported
   float* gather_peer[MAXR] = {};        // other ranks' staging buffers (IPC-mapped)
   void* gather_peer_base[MAXR] = {};
@@ -414,12 +416,33 @@ int launch_gradk(rltv_ctx* c) {
   return fail(RLTV_ERR_ARG, "unsupported MK");
 }
 
+// TV-alive mode: TV(u) stencils, the TV gradient term T and its step statistics (pyx:495-496, :517, :543); no-op otherwise
+int launch_tv_grad(rltv_ctx* c) {
+  if (c->params.mode != RLTV_MODE_MM_TV) return RLTV_OK;
+  dim3 grid((c->g.pitch / 4 + 255) / 256, c->g.own1 - c->g.own0, 3);
+  ProfScope p(c, F_UPDATE);
+  k_tv_grad<<<grid, 256, 0, c->stream>>>(c->g, c->st, c->u, c->ut, c->gbuf, c->tvut1, c->tvut2, c->img, c->params.lambd,
+                                         c->params.blind ? 1e-2f : 1e-6f, c->tbuf, c->inner_count & 1, c->inner_in_outer == 0 ? 1 : 0);
+  return RLTV_OK;
+}
+
 int launch_update(rltv_ctx* c) {
   dim3 grid((c->g.pitch / 4 + 255) / 256, c->g.own1 - c->g.own0, 3);
   ProfScope p(c, F_UPDATE);
   // chain path: this step's statistics are in slot (inner_count & 1); the update resets the other slot for the next step
-  const int slot = c->use_chain ? (c->inner_count & 1) : 0;
+  const bool tvm = c->params.mode == RLTV_MODE_MM_TV;
+  const int slot = (c->use_chain || tvm) ? (c->inner_count & 1) : 0;
   const int reset_slot = c->use_chain ? (slot ^ 1) : -1;
+  if (c->params.mode == RLTV_MODE_MM_TV) {
+    if (c->inner_in_outer == 0)
+      k_update_tv<true><<<grid, 256, 0, c->stream>>>(c->g, c->st, c->u, nullptr, c->ut, c->gbuf, c->tbuf, c->img, c->params.step_factor,
+                                                     c->params.lambd, c->params.blind, c->use_chain ? slot : 0, reset_slot, slot);
+    else
+      k_update_tv<false><<<grid, 256, 0, c->stream>>>(c->g, c->st, c->u, c->ut, nullptr, c->gbuf, c->tbuf, c->img, c->params.step_factor,
+                                                      c->params.lambd, c->params.blind, c->use_chain ? slot : 0, reset_slot, slot);
+    c->chain_ipk_valid = false;                            // the image changed: its packed spectra follow
+    return RLTV_OK;
+  }
   HaloPush hp{};
   if (c->side[0].peer_u || c->side[1].peer_u) {            // row band with at least one neighbour: push inside the update
     c->halo_seq += 1;
@@ -490,6 +513,7 @@ int chain_setup_t(rltv_ctx* c) {
     first[G] = int(pieces.size());
     if (ipk_rows * FFT_N >= (size_t(1) << 31)) return fail(RLTV_ERR_ARG, "frame too large for the chain kernel's piece table");
     cudaFree(c->chain_pieces); cudaFree(c->chain_first); cudaFree(c->chain_ipk);
+  cudaFree(c->tvut1); cudaFree(c->tvut2); cudaFree(c->tbuf);
     c->chain_pieces = nullptr; c->chain_first = nullptr; c->chain_ipk = nullptr;
     c->chain_npieces = int(pieces.size());
     c->chain_ipk_rows = ipk_rows;
@@ -662,6 +686,11 @@ int enqueue_phase(rltv_ctx* c, int phase) {
       // ut[:] = u.copy() (pyx:462) costs nothing here: the first inner step reads u where it would read ut (the
       // adjoint kernels get u twice, the chain kernel a flag) and its update kernel writes ut <- u_old on the fly
       c->inner_in_outer = 0;
+      if (c->params.mode == RLTV_MODE_MM_TV) {                     // TV(ut, ...) of pyx:464-465 (patched reference), ut == u here
+        dim3 grid((c->g.pitch / 4 + 255) / 256, c->g.own1 - c->g.own0, 3);
+        ProfScope p(c, F_STATS);
+        k_tv_maps<<<grid, 256, 0, c->stream>>>(c->g, c->st, c->u, c->params.blind ? 1e-2f : 1e-6f, c->tvut1, c->tvut2);
+      }
       return RLTV_OK;
     case RLTV_PH_GRAD:
       if (c->use_chain) {
@@ -672,13 +701,14 @@ int enqueue_phase(rltv_ctx* c, int phase) {
         if (!c->params.blind && c->white_owner && c->inner_in_outer == RLTV_INNER_ITER - 1)
           if ((rc = launch_conv_fwd_window(c)) != RLTV_OK) return rc;
         if ((rc = launch_chain(c, c->params.lambd)) != RLTV_OK) return rc;    // pyx:477-491, :519, :524 in one pass
-        return RLTV_OK;
+        return launch_tv_grad(c);
       }
       if ((rc = launch_conv_fwd(c)) != RLTV_OK) return rc;        // pyx:477-488
       c->ut_is_u = (c->inner_in_outer == 0);
       rc = launch_conv_adj(c, c->params.lambd);                   // pyx:490-491, :519, :524
       c->ut_is_u = false;
-      return rc;
+      if (rc != RLTV_OK) return rc;
+      return launch_tv_grad(c);
     case RLTV_PH_UPDATE:
       if ((rc = launch_update(c)) != RLTV_OK) return rc;          // pyx:527-531, :499-502, :552
       c->inner_count += 1;
@@ -898,6 +928,7 @@ int rltv_destroy(rltv_ctx* c) {
   for (auto p : d) cudaFree(p);
   cudaFree(c->Z); cudaFree(c->tw); cudaFree(c->st); cudaFree(c->counters); cudaFree(c->wspec); cudaFree(c->gkf_part);
   cudaFree(c->chain_pieces); cudaFree(c->chain_first); cudaFree(c->chain_ipk);
+  cudaFree(c->tvut1); cudaFree(c->tvut2); cudaFree(c->tbuf);
   if (c->h_st) cudaFreeHost(c->h_st);
   if (c->h_poll) cudaFreeHost(c->h_poll);
   for (auto& e : c->poll_ev) if (e) cudaEventDestroy(e);
@@ -994,6 +1025,16 @@ int rltv_begin(rltv_ctx* c, const rltv_params_t* p) {
   if (!p) return fail(RLTV_ERR_ARG, "null params");
   if (!c->uploaded) return fail(RLTV_ERR_STATE, "rltv_upload must precede rltv_begin/rltv_solve");
   if (p->iterations < 0) return fail(RLTV_ERR_ARG, "negative iteration count");
+  if (p->mode != RLTV_MODE_MM && p->mode != RLTV_MODE_MM_TV) return fail(RLTV_ERR_ARG, "unknown solver mode");
+  if (p->mode == RLTV_MODE_MM_TV) {
+    if (c->banded) return fail(RLTV_ERR_STATE, "the TV-alive mode needs a whole-frame context (the denoised image is not exchanged between row bands)");
+    const size_t pb = 3 * c->g.plane * sizeof(float);
+    if (!c->tvut1) {
+      CU(cudaMalloc(&c->tvut1, pb));
+      CU(cudaMalloc(&c->tvut2, pb));
+      CU(cudaMalloc(&c->tbuf, pb));
+    }
+  }
   c->params = *p;
   rc = setup_whiteness(c, p->top, p->bottom, p->left, p->right);
   if (rc) return rc;
@@ -1162,6 +1203,20 @@ int rltv_ipc_attach(rltv_ctx* c, int32_t peer_rank, const void* handle64, int32_
   }
   if (s.src_row < c->g.own0 || s.src_row + s.nrows > c->g.own1 || s.dst_row < 0 || s.dst_row + s.nrows > peer_row_hi - peer_row_lo)
     return fail(RLTV_ERR_ARG, "halo rows do not fit: every band must own at least 2*(MK/2) rows");
+  return RLTV_OK;
+}
+
+int rltv_download_image(rltv_ctx* c, float* image, size_t image_rs) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  const Geom& g = c->g;
+  if (!c->uploaded || c->banded || !image) return fail(RLTV_ERR_STATE, "needs an uploaded whole-frame context");
+  if (image_rs < size_t(g.N) * 12) return fail(RLTV_ERR_ARG, "image row stride smaller than a packed row");
+  k_planar_to_hwc<<<dim3(hwc_grid(g.N), g.M), 256, 0, c->stream>>>(c->img, g, g.P, g.P, g.M, g.N, c->staging, size_t(g.N) * 3);
+  c->launches++;
+  CU(cudaMemcpy2DAsync(image, image_rs, c->staging, size_t(g.N) * 12, size_t(g.N) * 12, g.M, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
   return RLTV_OK;
 }
 

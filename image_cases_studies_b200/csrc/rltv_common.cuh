@@ -35,6 +35,7 @@ struct State {
                            // (pyx:524; 6 contiguous int32 = one MAX all-reduce across row bands).  Slot 0 is THE slot of
                            // the two-kernel gradient path (reset by its forward kernel); the chain kernel alternates
                            // the slots by inner step and the update kernel resets the one the next step will use.
+  int tvmax[2][9];         // TV-alive mode (rltv_tvmode.cuh): [slot][0..2] max|G_c|, [3..5] max|T_c|, [6..8] max(image_c)
   float dt[3];             // last image step sizes
   float dtpsf;             // last PSF step size (pyx:574)
   double win_sum;          // whiteness window: sum, min, max of the residual (pyx:627-629)

@@ -12,6 +12,9 @@ __global__ void k_state_init(State* __restrict__ st) {
     const int s = threadIdx.x / 3, c = threadIdx.x % 3;
     st->smax[s][c] = ORD_LOWEST;
     st->smax[s][3 + c] = 0;
+    st->tvmax[s][c] = 0;
+    st->tvmax[s][3 + c] = 0;
+    st->tvmax[s][6 + c] = ORD_LOWEST;
   }
 }
 
@@ -24,12 +27,12 @@ __global__ void k_state_init(State* __restrict__ st) {
 // 24 B/px copy pass the update reads u only and WRITES the majoriser: ut <- u_old.  Same bytes as a normal step.
 // Row bands: the update kernel also does the halo exchange.  Threads that rewrite one of the first / last 2P owned rows
 // store the new values straight into the neighbour's halo rows as well (peer stores over NVLink); the CTA that completes
-// a side raises the neighbour's step-numbered flag; and the last CTA of the grid waits for the NEIGHBOURS' flags, so
-// that when this kernel ends the band's own halo rows are up to date for whatever reads u next.  (Round 1 did this in a
+// a side raises the neighbour's step-numbered flag; and one designated CTA waits for the NEIGHBOURS' flags, so that
+// when this kernel ends the band's own halo rows are up to date for whatever reads u next.  (Round 1 did this in a
 // separate copy kernel, k_halo_push: 22 us per inner step that did not shrink with the band.)
 struct HaloPush {
   HaloSide top, bot;
-  unsigned* counters;          // [0] top side, [1] bottom side, [2] whole grid
+  unsigned* counters;          // [0] top side, [1] bottom side
   const int* flag_from_top;    // raised by the band above when ITS rows have landed here (nullptr: no neighbour)
   const int* flag_from_bot;
   int seq;
@@ -91,25 +94,28 @@ k_update(Geom g, State* __restrict__ st, float* __restrict__ u, const float* __r
     if (active && be)
       *reinterpret_cast<float4*>(hp.bot.peer_u + size_t(c) * hp.bot.peer_plane + size_t(hp.bot.dst_row + Y - hp.bot.src_row) * g.pitch + X) =
           make_float4(o[0], o[1], o[2], o[3]);
-    __threadfence_system();          // this thread's peer stores are visible system-wide before any flag
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      if (te && atomicAdd(hp.counters + 0, 1u) == unsigned(gridDim.x * hp.top.nrows * 3 - 1)) {
-        hp.counters[0] = 0u;
-        __threadfence_system();
-        *reinterpret_cast<volatile int*>(hp.top.peer_flag) = hp.seq;
+    if (te || be) {                  // CTA-uniform: only the CTAs that pushed rows pay for the system-scope fence
+      __threadfence_system();        // this thread's peer stores are visible system-wide before any flag
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        if (te && atomicAdd(hp.counters + 0, 1u) == unsigned(gridDim.x * hp.top.nrows * 3 - 1)) {
+          hp.counters[0] = 0u;
+          __threadfence_system();
+          *reinterpret_cast<volatile int*>(hp.top.peer_flag) = hp.seq;
+        }
+        if (be && atomicAdd(hp.counters + 1, 1u) == unsigned(gridDim.x * hp.bot.nrows * 3 - 1)) {
+          hp.counters[1] = 0u;
+          __threadfence_system();
+          *reinterpret_cast<volatile int*>(hp.bot.peer_flag) = hp.seq;
+        }
       }
-      if (be && atomicAdd(hp.counters + 1, 1u) == unsigned(gridDim.x * hp.bot.nrows * 3 - 1)) {
-        hp.counters[1] = 0u;
-        __threadfence_system();
-        *reinterpret_cast<volatile int*>(hp.bot.peer_flag) = hp.seq;
-      }
-      if (atomicAdd(hp.counters + 2, 1u) == gridDim.x * gridDim.y * gridDim.z - 1) {
-        hp.counters[2] = 0u;
-        if (hp.flag_from_top) spin_until(hp.flag_from_top, hp.seq);
-        if (hp.flag_from_bot) spin_until(hp.flag_from_bot, hp.seq);
-        __threadfence_system();
-      }
+    }
+    // ONE designated CTA (the last one in launch order) does not leave before the neighbours' rows have landed here, so
+    // the kernel as a whole does not complete before that.  It depends on the NEIGHBOURS' update kernels only.
+    if (blockIdx.x == gridDim.x - 1 && blockIdx.y == gridDim.y - 1 && blockIdx.z == gridDim.z - 1 && threadIdx.x < 2) {
+      const int* f = threadIdx.x == 0 ? hp.flag_from_top : hp.flag_from_bot;
+      if (f) spin_until(f, hp.seq);
+      __threadfence_system();
     }
   }
 }

@@ -52,8 +52,14 @@ def clear_cache():
 
 
 def richardson_lucy_MM(image, u, psf, top, bottom, left, right, tau, M, N, C, MK, iterations, step_factor, lambd,
-                       blind=True, correlation=False, p=1., norm=1, order=2, priority=0, refocus=0):
-    """Richardson-Lucy blind / non-blind deconvolution by Majorization-Minimization (lib/deconvolution.pyx:341-675)."""
+                       blind=True, correlation=False, p=1., norm=1, order=2, priority=0, refocus=0, mode="mm"):
+    """Richardson-Lucy blind / non-blind deconvolution by Majorization-Minimization (lib/deconvolution.pyx:341-675).
+
+    ``mode`` is an extension (not an argument of the reference): "mm" -- the default -- is the reference's shipped
+    arithmetic, in which the TV regulariser is computed but never used; "mm_tv" runs the TV branches of
+    pyx:516-517 / :542-549 as they would if the commented ``TV(ut, ...)`` calls of pyx:464-465 were alive and wrote
+    ``TV_ut_L1`` / ``TV_ut_L2`` (pinned against a patched build of the reference, oracle/build_ref_tv.py).  As in that
+    code path the blurry ``image`` is then denoised IN PLACE."""
     global last_stats
     _check_buffer(image, "image")
     _check_buffer(u, "u")
@@ -70,9 +76,11 @@ def richardson_lucy_MM(image, u, psf, top, bottom, left, right, tau, M, N, C, MK
     pad = (u.shape[0] - M) // 2                                         # pyx:376
     s = _solver(M, N, MK)
     s.upload(image, u, psf)
-    params = Solver.make_params((top, bottom, left, right), tau, iterations, step_factor, lambd, blind, correlation)
+    params = Solver.make_params((top, bottom, left, right), tau, iterations, step_factor, lambd, blind, correlation, mode)
     last_stats = s.solve(params)
     s.download(u=u, psf_caller=psf if blind else None)
+    if mode == "mm_tv":
+        s.download_image(image)                                         # pyx:549 writes the caller's image
     if VERBOSE:
         it = last_stats["iterations"]
         if last_stats["stopped"]:

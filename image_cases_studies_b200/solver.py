@@ -105,10 +105,22 @@ class Solver:
 
     # -- running ------------------------------------------------------------------------------------
     @staticmethod
-    def make_params(window, tau, iterations, step_factor, lambd, blind, correlation=False) -> nat.Params:
+    def make_params(window, tau, iterations, step_factor, lambd, blind, correlation=False, mode="mm") -> nat.Params:
         top, bottom, left, right = (int(v) for v in window)
+        if mode not in ("mm", "mm_tv"):
+            raise ValueError("mode must be 'mm' (the reference's shipped arithmetic) or 'mm_tv' (TV term alive)")
         return nat.Params(top, bottom, left, right, float(tau), int(iterations), float(step_factor), float(lambd),
-                          int(bool(blind)), int(bool(correlation)))
+                          int(bool(blind)), int(bool(correlation)), nat.MODE_MM_TV if mode == "mm_tv" else nat.MODE_MM)
+
+    def download_image(self, image: np.ndarray) -> np.ndarray:
+        """The blurry image as it is on the device (mode="mm_tv" denoises it in place, pyx:547-549)."""
+        if image.shape != (self.M, self.N, 3):
+            raise ValueError("bad image shape")
+        t = image if (_rows_ok(image) and image.flags.writeable) else np.empty((self.M, self.N, 3), np.float32)
+        nat.check(nat.lib.rltv_download_image(self._ctx, nat.ptr(t), t.strides[0]))
+        if t is not image:
+            image[...] = t
+        return image
 
     def solve(self, params: nat.Params) -> dict:
         st = nat.Stats()

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define RLTV_ABI_VERSION 1
+#define RLTV_ABI_VERSION 2
 #define RLTV_INNER_ITER 5       /* pyx:375 */
 #define RLTV_MAX_MK 31          /* direct stencils are instantiated for odd MK in [3, 31] */
 #define RLTV_MAX_HISTORY 4096   /* outer iterations whose M_r is kept in rltv_stats_t.M_r_history */
@@ -51,7 +51,13 @@ typedef struct {
   float lambd;                      /* pyx:502, :519 */
   int32_t blind;                    /* pyx:555 */
   int32_t correlation;              /* pyx:584-585 (channel-mean PSF) */
+  int32_t mode;                     /* RLTV_MODE_MM: the reference's shipped arithmetic (TV term dead) -- the
+                                     * pinned drop-in.  RLTV_MODE_MM_TV: the TV branches of pyx:516-517 / :542-549 alive, as in
+                                     * the "patched reference" of oracle/build_ref_tv.py; the blurry image is denoised in place
+                                     * (read it back with rltv_download_image).  Whole-frame contexts only. */
 } rltv_params_t;
+#define RLTV_MODE_MM 0
+#define RLTV_MODE_MM_TV 1
 
 typedef struct {
   int32_t iterations_executed;      /* outer iterations run (pyx:656) */
@@ -153,6 +159,9 @@ void* rltv_device_ptr(rltv_ctx* ctx, const char* name, size_t* nbytes);
 /* deterministic host-side stop polling: record after outer iteration `it`, wait for iteration `it` */
 int rltv_poll_record(rltv_ctx* ctx, int32_t it);
 int rltv_poll_wait(rltv_ctx* ctx, int32_t it, int32_t* stop);
+
+/* the blurry image as it is on the device (the TV-alive mode denoises it in place, pyx:547-549) -> packed HWC (M,N,3) rows */
+int rltv_download_image(rltv_ctx* ctx, float* image, size_t image_row_stride_bytes);
 
 /* ---- gathering the result bands on the device ----------------------------------------------------------------
  * The destination rank allocates a full-frame HWC staging buffer (rltv_gather_alloc) and exports it over CUDA IPC;

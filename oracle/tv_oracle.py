@@ -6,9 +6,13 @@
 
 The solver calls it twice per inner step (``:495-496``) and discards the results; it is restated --
 and built as a CUDA kernel, ``rltv_stage_tv`` -- because SURVEY.md section 8(a) row a4 lists it on the path and the TV-alive
-modes (8(f3)) need it.  Pinned against the compiled reference? No: ``TV`` is a ``cdef inline`` function with no
-Python entry point, so it cannot be called from oracle/_ref; parity for this stencil is pinned to this restatement
-only ("parity unpinned by reference execution"), as DESIGN.md states.
+mode (8(f3), ``mode="mm_tv"``) needs it.
+
+PINNED by reference execution: ``TV`` is a ``cdef inline`` function with no Python entry point, so
+``oracle/build_ref_tv.py`` appends a ``cpdef`` wrapper to a COPY of the reference source and compiles that; the
+fixtures ``tests/golden/tv_o{1,2}n{1,2}.npz`` are outputs of the reference's own ``TV`` through that wrapper
+(``tests/golden/make_golden_tv.py``), and ``tests/test_oracle.py`` checks this restatement against them (agreement
+1e-7) and against the patched build live when it is present.
 """
 from __future__ import annotations
 

@@ -23,7 +23,18 @@ def psf_l1(a, b) -> float:
 
 
 def golden_names():
-    return sorted(p.stem for p in GOLDEN.glob("*.npz") if not p.stem.startswith("normalize"))
+    """Fixtures of the UNMODIFIED reference solver (tests/golden/make_golden.py)."""
+    return sorted(p.stem for p in GOLDEN.glob("*.npz") if not p.stem.startswith(("normalize", "tv_", "tvmm_")))
+
+
+def tv_golden_names():
+    """TV() stencil fixtures of the patched reference (tests/golden/make_golden_tv.py)."""
+    return sorted(p.stem for p in GOLDEN.glob("tv_*.npz"))
+
+
+def tvmm_golden_names():
+    """Solver fixtures of the patched reference with the TV term alive (tests/golden/make_golden_tv.py)."""
+    return sorted(p.stem for p in GOLDEN.glob("tvmm_*.npz"))
 
 
 def load_golden(name):

@@ -25,12 +25,12 @@ def test_header_symbols_all_exported_and_bound(nat):
     assert declared == bound, (declared ^ bound)
     for name in declared:
         assert hasattr(nat.lib, name)
-    assert nat.lib.rltv_abi_version() == 1
+    assert nat.lib.rltv_abi_version() == 2
 
 
 def test_struct_layouts_match_header(nat):
     import ctypes as C
-    assert C.sizeof(nat.Params) == 40
+    assert C.sizeof(nat.Params) == 44
     assert C.sizeof(nat.Stats) == 4 * (2 + 2 + 3 + 1 + 1 + 1 + 1) + 4 * nat.RLTV_MAX_HISTORY
 
 

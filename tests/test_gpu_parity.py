@@ -7,7 +7,7 @@ Tolerances (BASELINE.json north_star): image rel-L2 <= 1e-4, PSF L1 <= 1e-4, equ
 import numpy as np
 import pytest
 
-from helpers import TOL_IMAGE_REL_L2, TOL_PSF_L1, golden_names, load_golden, psf_l1, rel_l2
+from helpers import TOL_IMAGE_REL_L2, TOL_PSF_L1, golden_names, load_golden, psf_l1, rel_l2  # noqa: F401
 
 pytestmark = pytest.mark.gpu
 
@@ -393,3 +393,57 @@ def test_chain_kernel_against_oracle(K, shape):
         assert rel_l2(g[..., c], g_ref) < 2e-5, (c, rel_l2(g[..., c], g_ref))
         assert abs(mx[c] - u[..., c].max()) == 0
         assert abs(mx[3 + c] - np.abs(g_ref).max()) <= 1e-4 * np.abs(g_ref).max()
+
+
+@pytest.mark.parametrize("name", __import__("helpers").tv_golden_names())
+def test_tv_stencil_against_reference_executed_fixtures(name):
+    """rltv_stage_tv (k_tv<ORDER, NORM>) against the reference's OWN TV() (pyx:137-239) run through the cpdef wrapper of
+    oracle/build_ref_tv.py -- fixtures tests/golden/tv_o*n*.npz, all four (order, norm) pairs."""
+    from helpers import GOLDEN
+    from image_cases_studies_b200.solver import Solver
+    z = np.load(GOLDEN / f"{name}.npz")
+    u = z["u"]
+    K = 3
+    M, N = u.shape[0] - K + 1, u.shape[1] - K + 1
+    s = Solver(M, N, K)
+    s.upload(np.zeros((M, N, 3), np.float32), u, np.full((K, K, 3), 1 / 9, np.float32))
+    out, div = s.stage_tv(int(z["order"]), int(z["norm"]), float(z["epsilon"]))
+    s.close()
+    assert np.abs(out - z["ref_out"]).max() <= 2e-6 * np.abs(z["ref_out"]).max()
+    assert np.abs(div - z["ref_div"]).max() <= 2e-6 * np.abs(z["ref_div"]).max()
+
+
+@pytest.mark.parametrize("name", __import__("helpers").tvmm_golden_names())
+def test_tv_alive_mode_against_patched_reference(dc, name):
+    """mode="mm_tv" (k_tv_maps / k_tv_grad / k_update_tv) against the PATCHED reference with the TV(ut) calls of pyx:464-465
+    alive (oracle/build_ref_tv.py; fixtures tests/golden/tvmm_*.npz): estimate, PSF, the in-place denoised image."""
+    g = load_golden(name)
+    M, N = g["image"].shape[:2]
+    MK = g["psf0"].shape[0]
+    image, u, psf = g["image"].copy(), g["u0"].copy(), g["psf0"].copy()
+    out = dc.richardson_lucy_MM(image, u, psf, *g["window"], g["tau"], M, N, 3, MK, g["iterations"], g["step_factor"],
+                                g["lambd"], blind=g["blind"], mode="mm_tv")
+    assert dc.last_stats["iterations"] == g["ref_iterations"]
+    assert rel_l2(out, g["ref_out"]) <= TOL_IMAGE_REL_L2 and rel_l2(u, g["ref_u"]) <= TOL_IMAGE_REL_L2
+    assert rel_l2(image, g["ref_image"]) <= TOL_IMAGE_REL_L2 and not np.array_equal(image, g["image"])
+    assert psf_l1(psf, g["ref_psf"]) <= TOL_PSF_L1
+    # ... and it is a different result from the shipped arithmetic on the same inputs
+    u0, p0 = g["u0"].copy(), g["psf0"].copy()
+    dc.richardson_lucy_MM(g["image"].copy(), u0, p0, *g["window"], g["tau"], M, N, 3, MK, g["iterations"], g["step_factor"],
+                          g["lambd"], blind=g["blind"])
+    assert rel_l2(u0, g["ref_u"]) > 5e-4
+
+
+def test_tv_alive_mode_against_oracle_larger_frame(dc):
+    from image_cases_studies_b200 import synthetic
+    from oracle import rl_mm_oracle as orc
+    c = synthetic.make_case("c3_blind_24mp_k15", seed=17, scale=0.07, iterations=3)
+    M, N = c.shape
+    image, u, psf = c.image.copy(), c.u0.copy(), c.psf0.copy()
+    out = dc.richardson_lucy_MM(image, u, psf, *c.window, c.tau, M, N, 3, c.MK, c.iterations, c.step_factor, c.lambd,
+                                blind=True, mode="mm_tv")
+    ref = orc.richardson_lucy_MM(c.image, c.u0, c.psf0, *c.window, c.tau, M, N, 3, c.MK, c.iterations, c.step_factor, c.lambd,
+                                 blind=True, tv_alive=True)
+    assert dc.last_stats["iterations"] == ref.iterations
+    assert rel_l2(out, ref.out) <= TOL_IMAGE_REL_L2 and rel_l2(image, ref.image) <= TOL_IMAGE_REL_L2
+    assert psf_l1(psf, ref.psf) <= TOL_PSF_L1

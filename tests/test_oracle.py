@@ -104,3 +104,34 @@ def test_tv_oracle_against_pure_loop_definition():
                 assert abs(div[i, j, k] - (-udx - udy - udxdy - udydx) / adjust) < 1e-14
                 assert abs(out[i, j, k] - (abs(udx) + abs(udy) + 1e-2 + abs(udxdy) + abs(udydx) + 1e-2) / adjust) < 1e-14
     assert not out[0].any() and not div[:, -1].any()
+
+
+@pytest.mark.parametrize("name", __import__("helpers").tv_golden_names())
+def test_tv_oracle_against_reference_executed_fixtures(name):
+    """oracle/tv_oracle.py against the reference's OWN TV() (lib/deconvolution.pyx:137-239) run through the cpdef wrapper
+    that oracle/build_ref_tv.py appends to a copy of the source: all four (order, norm) pairs."""
+    from helpers import GOLDEN
+    from oracle import tv_oracle
+    z = np.load(GOLDEN / f"{name}.npz")
+    out, div = tv_oracle.tv(z["u"], float(z["epsilon"]), int(z["order"]), int(z["norm"]))
+    assert np.abs(out - z["ref_out"]).max() <= 5e-7 * np.abs(z["ref_out"]).max()
+    assert np.abs(div - z["ref_div"]).max() <= 5e-7 * np.abs(z["ref_div"]).max()
+    assert not z["ref_out"][0].any() and not z["ref_div"][:, -1].any()          # the reference leaves the ring at zero
+
+
+@pytest.mark.parametrize("name", __import__("helpers").tvmm_golden_names())
+def test_tv_alive_oracle_against_patched_reference_fixtures(name):
+    """rl_mm_oracle(tv_alive=True) against the PATCHED reference (TV(ut) calls of pyx:464-465 alive, oracle/build_ref_tv.py):
+    estimate, refined PSF, the in-place denoised blurry image and the iteration count."""
+    g = load_golden(name)
+    M, N = g["image"].shape[:2]
+    K = g["psf0"].shape[0]
+    r = orc.richardson_lucy_MM(g["image"], g["u0"], g["psf0"], *g["window"], g["tau"], M, N, 3, K, g["iterations"],
+                               g["step_factor"], g["lambd"], blind=g["blind"], tv_alive=True)
+    assert r.iterations == g["ref_iterations"]
+    assert rel_l2(r.u, g["ref_u"]) <= 5e-5 and rel_l2(r.image, g["ref_image"]) <= 5e-6
+    assert psf_l1(r.psf, g["ref_psf"]) <= 1e-5
+    # the TV term is not a no-op: the same inputs through the shipped (TV-dead) arithmetic end elsewhere
+    r0 = orc.richardson_lucy_MM(g["image"], g["u0"], g["psf0"], *g["window"], g["tau"], M, N, 3, K, g["iterations"],
+                                g["step_factor"], g["lambd"], blind=g["blind"])
+    assert rel_l2(r0.u, g["ref_u"]) > 5e-4
