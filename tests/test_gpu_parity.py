@@ -425,7 +425,9 @@ def test_tv_alive_mode_against_patched_reference(dc, name):
                                 g["lambd"], blind=g["blind"], mode="mm_tv")
     assert dc.last_stats["iterations"] == g["ref_iterations"]
     assert rel_l2(out, g["ref_out"]) <= TOL_IMAGE_REL_L2 and rel_l2(u, g["ref_u"]) <= TOL_IMAGE_REL_L2
-    assert rel_l2(image, g["ref_image"]) <= TOL_IMAGE_REL_L2 and not np.array_equal(image, g["image"])
+    assert rel_l2(image, g["ref_image"]) <= TOL_IMAGE_REL_L2
+    # (non-blind: epsilon = 1e-6 makes the image step ~1e-8 relative, below float32 resolution in the reference too)
+    assert np.array_equal(image, g["image"]) == np.array_equal(g["ref_image"], g["image"])
     assert psf_l1(psf, g["ref_psf"]) <= TOL_PSF_L1
     # ... and it is a different result from the shipped arithmetic on the same inputs
     u0, p0 = g["u0"].copy(), g["psf0"].copy()
