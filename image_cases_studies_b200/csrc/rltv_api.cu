@@ -93,6 +93,10 @@ struct rltv_ctx {
   bool chain_ipk_valid = false;
   int inner_count = 0;                  // inner steps enqueued since rltv_begin (statistics slot = parity)
   int inner_in_outer = 0;               // 0 right after ut = u
+  // CUDA graphs of one outer iteration (launch-bound frames): [parity of the first inner step's statistics slot]
+  cudaGraphExec_t outer_graph[2] = {nullptr, nullptr};
+  int outer_graph_launches = 0;         // kernel launches one replay stands for
+  bool use_graph = false;
   float *tvut1 = nullptr, *tvut2 = nullptr, *tbuf = nullptr;   // TV-alive mode: TV(ut) maps, T = TV gradient term
   float* gather_stage = nullptr;        // full-frame HWC staging buffer of THIS rank (device), IPC-exported
   float* gather_peer[MAXR] = {};        // other ranks' staging buffers (IPC-mapped)
@@ -764,6 +768,48 @@ int enqueue_outer(rltv_ctx* c) {
   return RLTV_OK;
 }
 
+void drop_graphs(rltv_ctx* c) {
+  for (auto& g : c->outer_graph)
+    if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+}
+
+// One outer iteration, replayed from a CUDA graph when the frame is small enough to be launch-bound (SURVEY.md section 7
+// step 7; the pyramid's 255-px crops, BASELINE config 1): ~20 launches of 8-17 us each collapse into one graph launch.
+// Everything a launch depends on is either constant within a solve or periodic in the parity of the inner-step counter
+// (the statistics slot), hence two graphs.  Row bands keep plain launches (their exchange numbers grow every step).
+int enqueue_outer_fast(rltv_ctx* c) {
+  if (!c->use_graph || c->prof || c->banded || c->outer_enqueued < 2) return enqueue_outer(c);
+  const int par = c->inner_count & 1;
+  if (!c->outer_graph[par]) {
+    cudaGraph_t graph = nullptr;
+    const long before = c->launches;
+    const int ic = c->inner_count, osb = c->outer_since_begin;
+    CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = enqueue_outer(c);
+    cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+    if (rc != RLTV_OK || e != cudaSuccess || !graph) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      c->use_graph = false;                                   // capture not possible here: plain launches from now on
+      c->inner_count = ic; c->outer_since_begin = osb; c->launches = before;
+      return enqueue_outer(c);
+    }
+    c->outer_graph_launches = int(c->launches - before);
+    e = cudaGraphInstantiate(&c->outer_graph[par], graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail(RLTV_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+    // the capture only recorded the work (and advanced the host-side counters): run it now
+    CU(cudaGraphLaunch(c->outer_graph[par], c->stream));
+    return RLTV_OK;
+  }
+  CU(cudaGraphLaunch(c->outer_graph[par], c->stream));
+  c->inner_count += RLTV_INNER_ITER;
+  c->inner_in_outer = RLTV_INNER_ITER;
+  c->outer_since_begin += 1;
+  c->launches += c->outer_graph_launches;
+  return RLTV_OK;
+}
+
 void fill_stats(rltv_ctx* c, rltv_stats_t* s, float ms) {
   if (!s) return;
   const State& h = *c->h_st;
@@ -918,6 +964,7 @@ int rltv_destroy(rltv_ctx* c) {
   if (!c) return RLTV_OK;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  drop_graphs(c);
   for (auto& pb : c->peer_base) if (pb) cudaIpcCloseMemHandle(pb);
   for (auto& pb : c->gather_peer_base) if (pb) cudaIpcCloseMemHandle(pb);
   cudaFree(c->gather_stage);
@@ -1036,6 +1083,12 @@ int rltv_begin(rltv_ctx* c, const rltv_params_t* p) {
     }
   }
   c->params = *p;
+  drop_graphs(c);                                  // kernel arguments of the previous solve are baked into them
+  {
+    const char* e = getenv("RLTV_GRAPH");
+    c->use_graph = !c->banded && size_t(c->g.M) * c->g.N <= (size_t(1) << 22);     // <= 4 MP: launch-bound
+    if (e) c->use_graph = atoi(e) != 0 && !c->banded;
+  }
   rc = setup_whiteness(c, p->top, p->bottom, p->left, p->right);
   if (rc) return rc;
   CU(cudaMemsetAsync(c->st, 0, sizeof(State), c->stream));
@@ -1064,7 +1117,7 @@ int rltv_enqueue_outer(rltv_ctx* c, int32_t n_outer) {
   if (!c->begun) return fail(RLTV_ERR_STATE, "rltv_begin must precede rltv_enqueue_outer");
   if (c->banded && !c->fused_comm) return fail(RLTV_ERR_STATE, "NCCL-baseline row bands are stepped phase by phase (rltv_enqueue_phase)");
   for (int i = 0; i < n_outer; ++i) {
-    if ((rc = enqueue_outer(c)) != RLTV_OK) return rc;
+    if ((rc = enqueue_outer_fast(c)) != RLTV_OK) return rc;
     c->outer_enqueued++;
   }
   return RLTV_OK;
@@ -1113,7 +1166,7 @@ int rltv_solve(rltv_ctx* c, const rltv_params_t* p, rltv_stats_t* stats) {
       if ((rc = rltv_poll_wait(c, it - 2, &stop)) != RLTV_OK) return rc;
       if (stop) break;
     }
-    if ((rc = enqueue_outer(c)) != RLTV_OK) return rc;
+    if ((rc = enqueue_outer_fast(c)) != RLTV_OK) return rc;
     c->outer_enqueued++;
     if ((rc = rltv_poll_record(c, it)) != RLTV_OK) return rc;
   }
