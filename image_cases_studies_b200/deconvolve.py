@@ -19,13 +19,11 @@ from .lib import utils
 
 
 def pad_image(image, pad, mode="edge"):
-    """deconvolve.py:24-37: pad the two spatial axes of an RGB image, return contiguous float32."""
-    if isinstance(pad, int):
-        pad = (pad, pad)
-    if not isinstance(pad[0], (tuple, list)):
-        pad = ((pad[0], pad[0]), (pad[1], pad[1])) if len(pad) == 2 and pad[0] != pad[1] else ((pad[0], pad[0]), (pad[0], pad[0]))
-    out = np.pad(image, (tuple(pad[0]), tuple(pad[1]), (0, 0)), mode=mode)
-    return np.ascontiguousarray(out, np.float32)
+    """deconvolve.py:24-37: pad the two spatial axes of an RGB image, return contiguous float32.  ``pad`` is handed to
+    ``np.pad`` per channel exactly as the reference does, so an int, a (before, after) pair and a per-axis pair of pairs
+    all mean what they mean there."""
+    planes = [np.pad(image[..., c], pad, mode=mode) for c in range(image.shape[2])]
+    return np.ascontiguousarray(np.stack(planes, axis=2), np.float32)
 
 
 def build_pyramid(psf_size, lambd):
