@@ -437,22 +437,30 @@ def main():
     conv_mode = os.environ.get("RLTV_CONV", "fft" if K >= 11 else "direct")
     fused_residual = case.blind and conv_mode == "fft" and K <= 17 and os.environ.get("RLTV_FUSE", "1") != "0"
     fam_bytes = dict(FAMILY_BYTES_PER_PX)
+    # 11 <= K <= 17: forward blur, residual and adjoint are ONE launch (k_chain_fft), timed under the conv_adj family:
+    # reads u, ut, image (as packed spectra), writes g
+    chain = conv_mode == "fft" and 11 <= K <= 17 and os.environ.get("RLTV_CHAIN", "1") != "0" and (world == 1 or args.comm == "fused")
+    if chain:
+        fam_bytes["conv_adj"] = 48.0
     if fused_residual:
         fam_bytes["gradk"] = 24.0        # the PSF-gradient kernel computes the residual itself: reads u and the image
     alg_bytes = fam_bytes[dom] * M * N * rows_frac
     # the row-FFT PSF gradient is two launches (accumulate + finish) timed under one family: report them per gradient
     gk_launches = 2 if conv_mode == "fft" else 1
+    if chain:
+        flops_note = "forward + adjoint in one launch"
     if prof["gradk"][1]:
         fam_ms["gradk"] = fam_tot["gradk"] / max(prof["gradk"][1] // gk_launches, 1)
     dom_ms = fam_ms[dom]
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms else 0.0
     fpk, fpk_src = fp32_peak()
-    flops_launch = 2.0 * 3 * K * K * M * N * rows_frac
+    flops_launch = 2.0 * 3 * K * K * M * N * rows_frac * (2.0 if (chain and dom == "conv_adj") else 1.0)
     step_bytes = BYTES_PER_PX_STEP[case.blind] * M * N * INNER
     ms_step = ms / args.steps
     # measured DRAM traffic of the same kernel: only meaningful for the whole frame on one GPU at the profiled size
     traffic, traffic_src = (ncu_traffic(case.name, dom) if (world == 1 and not args.frame and args.scale == 1.0) else (None, None))
-    roofline = {"bound": "hbm", "kernel": f"{dom}<{K}>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+    kname = {"conv_adj": "chain" if chain else "conv_adj"}.get(dom, dom)
+    roofline = {"bound": "hbm", "kernel": f"{kname}<{K}>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": dom_ms,
                 "share_of_step": fam_tot[dom] / tot,

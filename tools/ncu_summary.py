@@ -14,7 +14,7 @@ KEYS = [("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "dram_rd"),
         ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem_conflicts"), ("lts__t_bytes.sum", "l2_bytes")]
 
 
-FAMILIES = [("k_conv_fft<", ", 0>", "conv_fwd"), ("k_conv_fft<", ", 1>", "conv_adj"), ("k_conv<", ", 0>", "conv_fwd"),
+FAMILIES = [("k_chain_fft<", "", "conv_adj"), ("k_conv_fft<", ", 0>", "conv_fwd"), ("k_conv_fft<", ", 1>", "conv_adj"), ("k_conv<", ", 0>", "conv_fwd"),
             ("k_conv<", ", 1>", "conv_adj"), ("k_update", "", "update"), ("k_gradk_fft<", "", "gradk"), ("k_gradk<", "", "gradk")]
 
 
