@@ -16,7 +16,7 @@ PKG = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ["RLTV_LIB"]) if os.environ.get("RLTV_LIB") else PKG / "librltv_b200.so"
 
 RLTV_MAX_HISTORY = 4096
-RLTV_MAX_MK = 31
+RLTV_MAX_MK = 47
 INNER_ITER = 5
 MODE_MM, MODE_MM_TV = 0, 1
 

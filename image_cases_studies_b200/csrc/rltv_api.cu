@@ -51,6 +51,8 @@ int fail(int code, const std::string& msg) {
       return fail(RLTV_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));             \
   } while (0)
 
+constexpr int RLTV_MAX_DIRECT_MK = 31;
+
 enum Family { F_CONV_FWD = 0, F_CONV_ADJ, F_UPDATE, F_GRADK, F_PSF, F_STATS, F_COPY, F_HALO, F_COUNT };
 const char* kFamilyNames[F_COUNT] = {"conv_fwd", "conv_adj", "update", "gradk", "psf", "stats", "copy", "halo"};
 
@@ -186,7 +188,8 @@ void prof_collect(rltv_ctx* c) {
 #define RLTV_FOR_EACH_K(M) RLTV_K_LIST
 #else
 #define RLTV_FOR_EACH_K(M) \
-  M(3) M(5) M(7) M(9) M(11) M(13) M(15) M(17) M(19) M(21) M(23) M(25) M(27) M(29) M(31)
+  M(3) M(5) M(7) M(9) M(11) M(13) M(15) M(17) M(19) M(21) M(23) M(25) M(27) M(29) M(31) \
+  M(33) M(35) M(37) M(39) M(41) M(43) M(45) M(47)
 #endif
 
 // ---- TMA descriptors ---------------------------------------------------------------------------------
@@ -223,18 +226,20 @@ int make_tmap(CUtensorMap* tm, float* base, const Geom& g, int rows, int bw, int
 
 template <int K>
 int make_maps_t(rltv_ctx* c) {
-  using C = ConvCfg<K>;
-  using G = GradkCfg<K>;
   const Geom& g = c->g;
   int rc;
-  if ((rc = make_tmap(&c->tm_u_conv, c->u, g, g.Hu, C::SP, C::SROWS))) return rc;
-  if ((rc = make_tmap(&c->tm_err_conv, c->err, g, g.Hu, C::SP, C::SROWS))) return rc;
-  if ((rc = make_tmap(&c->tm_img_epi, c->img, g, g.Hu, C::TW, C::TH))) return rc;
-  if ((rc = make_tmap(&c->tm_u_epi, c->u, g, g.Hu, C::TW, C::TH))) return rc;
-  if ((rc = make_tmap(&c->tm_ut_epi, c->ut, g, g.Hu, C::TW, C::TH))) return rc;
-  if ((rc = make_tmap(&c->tm_u_gk, c->u, g, g.Hu, G::SP, G::SROWS))) return rc;
-  // residual as seen by the PSF gradient: OWNED rows only (halo rows read as zero)
-  if ((rc = make_tmap(&c->tm_err_gk, c->err + size_t(g.own0) * g.pitch, g, g.own1 - g.own0, G::TW, G::TH))) return rc;
+  if constexpr (K <= RLTV_MAX_DIRECT_MK) {       // direct stencils exist up to 31 x 31
+    using C = ConvCfg<K>;
+    using G = GradkCfg<K>;
+    if ((rc = make_tmap(&c->tm_u_conv, c->u, g, g.Hu, C::SP, C::SROWS))) return rc;
+    if ((rc = make_tmap(&c->tm_err_conv, c->err, g, g.Hu, C::SP, C::SROWS))) return rc;
+    if ((rc = make_tmap(&c->tm_img_epi, c->img, g, g.Hu, C::TW, C::TH))) return rc;
+    if ((rc = make_tmap(&c->tm_u_epi, c->u, g, g.Hu, C::TW, C::TH))) return rc;
+    if ((rc = make_tmap(&c->tm_ut_epi, c->ut, g, g.Hu, C::TW, C::TH))) return rc;
+    if ((rc = make_tmap(&c->tm_u_gk, c->u, g, g.Hu, G::SP, G::SROWS))) return rc;
+    // residual as seen by the PSF gradient: OWNED rows only (halo rows read as zero)
+    if ((rc = make_tmap(&c->tm_err_gk, c->err + size_t(g.own0) * g.pitch, g, g.own1 - g.own0, G::TW, G::TH))) return rc;
+  }
   if constexpr (K >= 9) {
     using F = FftCfg<K>;
     if ((rc = make_tmap(&c->tm_u_fft, c->u, g, g.Hu, F::INW, F::IN_ROWS))) return rc;
@@ -318,6 +323,7 @@ int launch_psf_spectrum(rltv_ctx* c) {
 template <int K, bool ADJ>
 int launch_conv_t(rltv_ctx* c, float lambd) {
   if (c->use_fft) return launch_conv_fft_t<K, ADJ>(c, lambd);
+  if constexpr (K <= RLTV_MAX_DIRECT_MK) {
   using C = ConvCfg<K>;
   constexpr int SMEM = C::smem_bytes(ADJ);
   CU(cudaFuncSetAttribute(k_conv<K, ADJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -335,6 +341,9 @@ int launch_conv_t(rltv_ctx* c, float lambd) {
                                                            lambd, c->err, ntx, nty, y0, y1, c->peers, 0, c->counters + 1);
   }
   return RLTV_OK;
+  } else {
+    return fail(RLTV_ERR_ARG, "direct stencils exist for MK <= 31");
+  }
 }
 
 template <int K>
@@ -365,6 +374,7 @@ int launch_gradk_fft_t(rltv_ctx* c) {
       // entry point asked for the gradient only
       const int fold = (c->fold_psf_step && !(c->banded && !c->fused_comm)) ? 1 : 0;
       c->psf_step_folded = fold != 0;
+      CU(cudaFuncSetAttribute(k_gradk_fft_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, int(6 * RLTV_MAX_MK * RLTV_MAX_MK * sizeof(float))));
       k_gradk_fft_finish<<<3 * K, 512, fold ? 6 * K * K * sizeof(float) : 0, c->stream>>>(
           c->st, c->gkf_part, c->gk_nparts, K, c->gk_sum, c->peers, c->gk_seq, c->counters + 2, fold, c->params.step_factor,
           c->params.correlation, c->psf, c->psf_caller, c->wspec);
@@ -378,6 +388,7 @@ int launch_gradk_fft_t(rltv_ctx* c) {
 template <int K>
 int launch_gradk_t(rltv_ctx* c) {
   if (c->use_fft_gradk) return launch_gradk_fft_t<K>(c);
+  if constexpr (K <= RLTV_MAX_DIRECT_MK) {
   using C = GradkCfg<K>;
   CU(cudaFuncSetAttribute(k_gradk<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   const int ntx = (c->g.Wu + C::TW - 1) / C::TW, nty = (c->g.own1 - c->g.own0 + C::TH - 1) / C::TH;
@@ -386,6 +397,9 @@ int launch_gradk_t(rltv_ctx* c) {
   k_gradk<K><<<c->gk_nparts, C::THREADS, C::SMEM_BYTES, c->stream>>>(c->tm_u_gk, c->tm_err_gk, c->g, c->st, c->gk_partial, ntx, nty,
                                                                      c->gk_sum, c->peers, c->gk_seq, c->counters + 2);
   return RLTV_OK;
+  } else {
+    return fail(RLTV_ERR_ARG, "direct stencils exist for MK <= 31");
+  }
 }
 
 int make_maps(rltv_ctx* c) {
@@ -583,6 +597,7 @@ int launch_psf_update(rltv_ctx* c) {
   const int K = c->g.K;
   {
     ProfScope p2(c, F_PSF);
+    CU(cudaFuncSetAttribute(k_psf_update, cudaFuncAttributeMaxDynamicSharedMemorySize, int(6 * RLTV_MAX_MK * RLTV_MAX_MK * sizeof(float))));
     k_psf_update<<<1, 256, 6 * K * K * sizeof(float), c->stream>>>(c->st, c->gk_sum, K, c->params.step_factor,
                                                                   c->params.correlation, c->psf, c->psf_caller,
                                                                   c->peers.peer[c->rank], c->peers.nranks, c->gk_seq);
@@ -864,7 +879,7 @@ int rltv_device_count(void) {
 int rltv_create_band(rltv_ctx** out, int32_t device, int32_t M, int32_t N, int32_t MK, const rltv_band_t* band, void* stream) {
   if (!out) return fail(RLTV_ERR_ARG, "null out pointer");
   *out = nullptr;
-  if (MK < 3 || (MK % 2) == 0 || MK > RLTV_MAX_MK) return fail(RLTV_ERR_ARG, "MK must be odd and in [3, 31]");
+  if (MK < 3 || (MK % 2) == 0 || MK > RLTV_MAX_MK) return fail(RLTV_ERR_ARG, "MK must be odd and in [3, 47]");
   if (M < 1 || N < 1) return fail(RLTV_ERR_ARG, "empty image");
   const int HuG = M + MK - 1, P = MK / 2;
   rltv_band_t b = band ? *band : rltv_band_t{0, HuG, 0, HuG};
@@ -940,7 +955,7 @@ int rltv_create_band(rltv_ctx** out, int32_t device, int32_t M, int32_t N, int32
     // Row-FFT hybrid stencils (csrc/rltv_stencil_fft.cuh) for the FP32-bound sizes; RLTV_CONV=direct|fft overrides
     const char* e = getenv("RLTV_CONV");
     c->use_fft = (MK >= 11);
-    if (e && !strcmp(e, "direct")) c->use_fft = false;
+    if (e && !strcmp(e, "direct") && MK <= RLTV_MAX_DIRECT_MK) c->use_fft = false;
     if (e && !strcmp(e, "fft") && MK >= 9) c->use_fft = true;
     c->use_fft_gradk = c->use_fft;
     c->fuse_residual = c->use_fft_gradk && MK <= 17;             // GradkFftCfg<K>::CAN_FUSE

@@ -20,7 +20,7 @@
 namespace rltv {
 
 constexpr int MAXR = 8;             // GPUs of one box
-constexpr int MAXKK = 31 * 31;
+constexpr int MAXKK = 47 * 47;   // RLTV_MAX_MK squared
 
 // Lives at the tail of every band's u allocation (one IPC handle maps the band and its Comm block).
 struct Comm {

@@ -1,4 +1,4 @@
-// Row-FFT hybrid stencils for 9 <= K <= 31 (forward blur, adjoint) and 9 <= K <= 17 (PSF gradient): the FLOP-reducing form of the forward blur and the adjoint
+// Row-FFT hybrid stencils for 9 <= K <= 47 (forward blur, adjoint, PSF gradient; fused residual up to K = 17): the FLOP-reducing form of the forward blur and the adjoint
 // (lib/deconvolution.pyx:477-491, :557-565), which the reference itself evaluates as FFT convolutions (scipy).
 //
 // A K x K stencil  out[Y][X] = sum_{ky,kx} w[ky][kx] in[Y-P+ky][X-P+kx]  costs K*K FMAs per output directly.  Here the
@@ -16,6 +16,7 @@
 //   3. inverse FFT of the 24 packed output rows
 //   4. epilogue as in k_conv (residual / step statistics), 112 columns x 48 rows, operands prefetched to registers
 #pragma once
+#include "../../include/rltv_b200.h"
 #include "rltv_band.cuh"
 #include "rltv_common.cuh"
 #include "rltv_elementwise.cuh"
@@ -27,10 +28,12 @@ namespace rltv {
 
 template <int K>
 struct FftCfg {
-  static_assert(K >= 9 && K <= 31, "128-sample segments: 112 outputs + halo up to K = 17, 96 outputs up to K = 31");
+  static_assert(K >= 9 && K <= RLTV_MAX_MK, "128-sample segments: 112 outputs + halo up to K = 17, 96 up to 33, fewer above");
   static constexpr int P = K / 2;
   static constexpr int P4 = (P + 3) & ~3;          // 16-byte aligned TMA box start
-  static constexpr int TWO = (K <= 17) ? 112 : 96; // valid output columns per 128-sample segment
+  // valid output columns per 128-sample segment: what the circular convolution leaves, in multiples of 8
+  static constexpr int TWO_MAX = ((FFT_N - P4 - P) / 8) * 8;
+  static constexpr int TWO = (K <= 17) ? 112 : (TWO_MAX < 96 ? TWO_MAX : 96);
   static constexpr int CTAS_PER_SM = (K <= 17) ? 2 : 1;
   static constexpr int HB = 24;                    // rows per packed block (real part: rows 0..23, imaginary: 24..47)
   static constexpr int TROWS = 2 * HB;
@@ -39,7 +42,9 @@ struct FftCfg {
   static constexpr int THREADS = 384;              // 12 warps; two CTAs per SM run their phases out of step
   static constexpr int NCHUNK = THREADS / FFT_N;   // MAC: 128 bins x 3 row chunks
   static constexpr int CHUNK = HB / NCHUNK;        // output rows per MAC thread
-  static constexpr int ER = THREADS / (TWO / 2);   // epilogue: 6 row slots x 56 column pairs
+  // epilogue: ER row slots x TWO/2 column pairs; ER = the largest divisor of HB the thread count covers
+  static constexpr int ER_MAX = THREADS / (TWO / 2);
+  static constexpr int ER = ER_MAX >= 12 ? 12 : (ER_MAX >= 8 ? 8 : 6);
   static constexpr int NTASK = HB / ER;
   // TMA box = INW x IN_ROWS floats.  INW = 136 (not 128): consecutive rows then start 8 banks apart, so the four rows
   // a warp transforms read the dense TMA buffer conflict-free with compile-time offsets (no per-row fetch rotation).
@@ -324,11 +329,11 @@ namespace rltv {
 // ------------------------------------------------------------------------------------------------
 template <int K>
 struct GradkFftCfg {
-  static_assert(K >= 9 && K <= 31, "see FftCfg");
+  static_assert(K >= 9 && K <= RLTV_MAX_MK, "see FftCfg");
   static constexpr int P = K / 2;
   static constexpr int P4 = (P + 3) & ~3;
-  static constexpr int TWO = (K <= 17) ? 112 : 96;
-  static constexpr int HB = (K <= 17) ? 40 : 32;
+  static constexpr int TWO = FftCfg<K>::TWO;
+  static constexpr int HB = (K <= 17) ? 40 : (K <= 31 ? 32 : 24);   // shared memory: (HB + K - 1) spectra rows of u
   static constexpr int THREADS = (K <= 17) ? 512 : 256;   // large K: 2K complex accumulators + a K-deep window per thread
   static constexpr int TROWS = 2 * HB;
   static constexpr int U_ROWS = TROWS + K - 1;      // real u rows per tile
@@ -635,27 +640,29 @@ k_gradk_fft_finish(State* __restrict__ st, const float2* __restrict__ part, int 
     A[k] = make_double2(0.5 * (a.x + c.x), 0.5 * (a.y - c.y));
   }
   __syncthreads();
-  // lag dx - P by 16 threads: 8 bins each, then a fixed xor tree
-  const int dx = tid >> 4, j = tid & 15;
-  double acc = 0.0;
-  if (dx < K) {
-    const int s = dx - P;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int kk = j * 8 + i;
-      const double2 a = A[kk], w = tw64[(kk * s) & (FFT_N - 1)];
-      acc += a.x * w.x - a.y * w.y;                            // Re(A[k] e^{+2 pi i k s / N})
-    }
-  }
-#pragma unroll
-  for (int m = 1; m < 16; m <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+  // lag dx - P by 16 threads: 8 bins each, then a fixed xor tree (32 lags per pass of the 512 threads)
   const int par = seq & 1;
-  if (dx < K && j == 0) {
-    const double sum = acc * (1.0 / double(FFT_N));
-    const int o = row * K + dx;
-    gk_sum[o] = sum;
-    if (cp.nranks > 1)
-      for (int rr = 0; rr < cp.nranks; ++rr) cp.peer[rr]->gk_val[par][cp.rank][o] = sum;
+  for (int dx0 = 0; dx0 < K; dx0 += 32) {
+    const int dx = dx0 + (tid >> 4), j = tid & 15;
+    double acc = 0.0;
+    if (dx < K) {
+      const int s = dx - P;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int kk = j * 8 + i;
+        const double2 a = A[kk], w = tw64[(kk * s) & (FFT_N - 1)];
+        acc += a.x * w.x - a.y * w.y;                            // Re(A[k] e^{+2 pi i k s / N})
+      }
+    }
+#pragma unroll
+    for (int m = 1; m < 16; m <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+    if (dx < K && j == 0) {
+      const double sum = acc * (1.0 / double(FFT_N));
+      const int o = row * K + dx;
+      gk_sum[o] = sum;
+      if (cp.nranks > 1)
+        for (int rr = 0; rr < cp.nranks; ++rr) cp.peer[rr]->gk_val[par][cp.rank][o] = sum;
+    }
   }
   if (cp.nranks > 1 || fold) {
     __shared__ int s_last;

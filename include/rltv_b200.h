@@ -31,7 +31,8 @@ extern "C" {
 
 #define RLTV_ABI_VERSION 2
 #define RLTV_INNER_ITER 5       /* pyx:375 */
-#define RLTV_MAX_MK 31          /* direct stencils are instantiated for odd MK in [3, 31] */
+#define RLTV_MAX_MK 47          /* odd MK in [3, 47]: direct stencils up to 9, chain kernel 11..17, row-FFT stencils above
+                                 * (the reference itself has no cap; its own job list goes up to 45, deconvolve.py:409) */
 #define RLTV_MAX_HISTORY 4096   /* outer iterations whose M_r is kept in rltv_stats_t.M_r_history */
 
 typedef enum {

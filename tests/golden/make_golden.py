@@ -60,6 +60,11 @@ CASES = {
                         dict(tau=0.0, iterations=2, step_factor=1e-3, lambd=1e4, blind=True)),
     "blind_100x100_k31": (lambda: white_case(100, 100, 31, utils.gaussian_kernel(31, 6.0), True, 26),
                           dict(tau=0.0, iterations=2, step_factor=1e-3, lambd=1e4, blind=True)),
+    # K > 31 (the reference's own job list goes up to 45, deconvolve.py:409): row-FFT stencils with 80 / 96-column segments
+    "blind_120x110_k45": (lambda: white_case(120, 110, 45, utils.gaussian_kernel(45, 8.0), True, 27),
+                          dict(tau=0.0, iterations=2, step_factor=1e-3, lambd=1e4, blind=True)),
+    "nonblind_104x128_k33": (lambda: white_case(104, 128, 33, utils.gaussian_kernel(33, 6.0), False, 28),
+                             dict(tau=1.0, iterations=2, step_factor=1e-3, lambd=1e4, blind=False)),
     "nonblind_stop_80x96_k7": (lambda: smooth_case(80, 96, 7, False, 0),
                                dict(tau=0.0, iterations=30, step_factor=1e-3, lambd=1e4, blind=False)),
     "nonblind_stop2_80x96_k7": (lambda: smooth_case(80, 96, 7, False, 1),

