@@ -18,7 +18,7 @@ LIB_PATH = Path(os.environ["RLTV_LIB"]) if os.environ.get("RLTV_LIB") else PKG /
 RLTV_MAX_HISTORY = 4096
 RLTV_MAX_MK = 47
 INNER_ITER = 5
-MODE_MM, MODE_MM_TV = 0, 1
+MODE_MM, MODE_MM_TV, MODE_PAM_CTV = 0, 1, 2
 
 
 class Params(C.Structure):

@@ -437,6 +437,12 @@ int launch_gradk(rltv_ctx* c) {
 
 // TV-alive mode: TV(u) stencils, the TV gradient term T and its step statistics (pyx:495-496, :517, :543); no-op otherwise
 int launch_tv_grad(rltv_ctx* c) {
+  if (c->params.mode == RLTV_MODE_PAM_CTV) {       // unpinned extension: collaborative TV sub-gradient, one pass
+    dim3 grid((c->g.pitch / 4 + 255) / 256, c->g.own1 - c->g.own0, 1);
+    ProfScope p(c, F_UPDATE);
+    k_ctv_grad<<<grid, 256, 0, c->stream>>>(c->g, c->st, c->u, c->gbuf, c->params.lambd, 1e-3f, c->tbuf, c->inner_count & 1);
+    return RLTV_OK;
+  }
   if (c->params.mode != RLTV_MODE_MM_TV) return RLTV_OK;
   dim3 grid((c->g.pitch / 4 + 255) / 256, c->g.own1 - c->g.own0, 3);
   ProfScope p(c, F_UPDATE);
@@ -449,15 +455,24 @@ int launch_update(rltv_ctx* c) {
   dim3 grid((c->g.pitch / 4 + 255) / 256, c->g.own1 - c->g.own0, 3);
   ProfScope p(c, F_UPDATE);
   // chain path: this step's statistics are in slot (inner_count & 1); the update resets the other slot for the next step
-  const bool tvm = c->params.mode == RLTV_MODE_MM_TV;
+  const bool tvm = c->params.mode != RLTV_MODE_MM;
   const int slot = (c->use_chain || tvm) ? (c->inner_count & 1) : 0;
   const int reset_slot = c->use_chain ? (slot ^ 1) : -1;
+  if (c->params.mode == RLTV_MODE_PAM_CTV) {
+    if (c->inner_in_outer == 0)
+      k_update_tv<true, true><<<grid, 256, 0, c->stream>>>(c->g, c->st, c->u, nullptr, c->ut, c->gbuf, c->tbuf, c->img, c->params.step_factor,
+                                                           c->params.lambd, c->params.blind, c->use_chain ? slot : 0, reset_slot, slot);
+    else
+      k_update_tv<false, true><<<grid, 256, 0, c->stream>>>(c->g, c->st, c->u, c->ut, nullptr, c->gbuf, c->tbuf, c->img, c->params.step_factor,
+                                                            c->params.lambd, c->params.blind, c->use_chain ? slot : 0, reset_slot, slot);
+    return RLTV_OK;
+  }
   if (c->params.mode == RLTV_MODE_MM_TV) {
     if (c->inner_in_outer == 0)
-      k_update_tv<true><<<grid, 256, 0, c->stream>>>(c->g, c->st, c->u, nullptr, c->ut, c->gbuf, c->tbuf, c->img, c->params.step_factor,
+      k_update_tv<true, false><<<grid, 256, 0, c->stream>>>(c->g, c->st, c->u, nullptr, c->ut, c->gbuf, c->tbuf, c->img, c->params.step_factor,
                                                      c->params.lambd, c->params.blind, c->use_chain ? slot : 0, reset_slot, slot);
     else
-      k_update_tv<false><<<grid, 256, 0, c->stream>>>(c->g, c->st, c->u, c->ut, nullptr, c->gbuf, c->tbuf, c->img, c->params.step_factor,
+      k_update_tv<false, false><<<grid, 256, 0, c->stream>>>(c->g, c->st, c->u, c->ut, nullptr, c->gbuf, c->tbuf, c->img, c->params.step_factor,
                                                       c->params.lambd, c->params.blind, c->use_chain ? slot : 0, reset_slot, slot);
     c->chain_ipk_valid = false;                            // the image changed: its packed spectra follow
     return RLTV_OK;
@@ -1093,9 +1108,9 @@ int rltv_begin(rltv_ctx* c, const rltv_params_t* p) {
   if (!p) return fail(RLTV_ERR_ARG, "null params");
   if (!c->uploaded) return fail(RLTV_ERR_STATE, "rltv_upload must precede rltv_begin/rltv_solve");
   if (p->iterations < 0) return fail(RLTV_ERR_ARG, "negative iteration count");
-  if (p->mode != RLTV_MODE_MM && p->mode != RLTV_MODE_MM_TV) return fail(RLTV_ERR_ARG, "unknown solver mode");
-  if (p->mode == RLTV_MODE_MM_TV) {
-    if (c->banded) return fail(RLTV_ERR_STATE, "the TV-alive mode needs a whole-frame context (the denoised image is not exchanged between row bands)");
+  if (p->mode != RLTV_MODE_MM && p->mode != RLTV_MODE_MM_TV && p->mode != RLTV_MODE_PAM_CTV) return fail(RLTV_ERR_ARG, "unknown solver mode");
+  if (p->mode != RLTV_MODE_MM) {
+    if (c->banded) return fail(RLTV_ERR_STATE, "the TV-alive modes need a whole-frame context (the denoised image is not exchanged between row bands)");
     const size_t pb = 3 * c->g.plane * sizeof(float);
     if (!c->tvut1) {
       CU(cudaMalloc(&c->tvut1, pb));

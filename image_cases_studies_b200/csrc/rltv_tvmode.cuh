@@ -134,7 +134,8 @@ k_tv_grad(Geom g, State* __restrict__ st, const float* __restrict__ u, const flo
   }
 }
 
-template <bool FIRST>
+// PAM = true (mode "pam_ctv"): G = T + lambda g (no majoriser term), the image is left alone.
+template <bool FIRST, bool PAM>
 __global__ void __launch_bounds__(256)
 k_update_tv(Geom g, State* __restrict__ st, float* __restrict__ u, const float* __restrict__ ut, float* __restrict__ ut_out,
             const float* __restrict__ gbuf, const float* __restrict__ tbuf, float* __restrict__ img, float step, float lambd,
@@ -171,21 +172,95 @@ k_update_tv(Geom g, State* __restrict__ st, float* __restrict__ u, const float* 
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const bool in = tv_inner(g, gy, X + i);
-    const float G = in ? (TT[i] + fmaf(lambd, gg[i], (uu[i] - tt[i]) / 4.f)) : fmaf(lambd, gg[i], 0.5f * (uu[i] - tt[i]));
+    const float G = PAM ? fmaf(lambd, gg[i], TT[i])
+                        : (in ? (TT[i] + fmaf(lambd, gg[i], (uu[i] - tt[i]) / 4.f)) : fmaf(lambd, gg[i], 0.5f * (uu[i] - tt[i])));
     float un = fmaf(-dt, G, uu[i]);
     io[i] = ii[i];
     if (rowin && (X + i) >= g.P && (X + i) < g.P + g.N) {
       const float d = (gg[i] - ii[i]) / (gg[i] + ii[i]);                 // DoF from the image BEFORE its update, pyx:499
       float dof = d * d;
       if (!blind) dof = dof / lambd;
-      io[i] = ii[i] - dti * TT[i] / lambd;                               // pyx:549
+      if (!PAM) io[i] = ii[i] - dti * TT[i] / lambd;                     // pyx:549
       un = (1.f - dof) * un + dof * io[i];                               // pyx:552
     }
     o[i] = ((X + i) < g.Wu) ? un : uu[i];
   }
   *reinterpret_cast<float4*>(u + off) = make_float4(o[0], o[1], o[2], o[3]);
-  *reinterpret_cast<float4*>(img + off) = make_float4(io[0], io[1], io[2], io[3]);
+  if (!PAM) *reinterpret_cast<float4*>(img + off) = make_float4(io[0], io[1], io[2], io[3]);
   if (FIRST) *reinterpret_cast<float4*>(ut_out + off) = uv;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// mode "pam_ctv" -- UNPINNED (no reference code exists: README.md:42-44, :113-117 only; definition in oracle/ctv_oracle.py)
+// Forward-difference gradients of the three channels, the collaborative l^{inf,1,1} weight (per pixel and derivative
+// direction only the channel with the largest |difference| carries the sub-gradient, floored at eps) and the divergence,
+// in ONE pass over u:   T = -div p,  and the step statistic max|lambda g_c + T_c| of the PAM u-step.
+// One thread = 4 adjacent pixels x 3 channels.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ctv_field(const float (&d)[3], float eps, float (&p)[3]) {
+  const float a0 = fabsf(d[0]), a1 = fabsf(d[1]), a2 = fabsf(d[2]);
+  const int cs = (a0 >= a1 && a0 >= a2) ? 0 : ((a1 >= a2) ? 1 : 2);          // first channel attaining the maximum
+#pragma unroll
+  for (int c = 0; c < 3; ++c) p[c] = (c == cs) ? d[c] / fmaxf(eps, fabsf(d[c])) : 0.f;
+}
+
+__global__ void __launch_bounds__(256)
+k_ctv_grad(Geom g, State* __restrict__ st, const float* __restrict__ u, const float* __restrict__ gbuf, float lambd, float eps,
+           float* __restrict__ tbuf, int slot) {
+  if (st->stop) return;
+  const int Y = g.own0 + blockIdx.y, X = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+  float mG[3] = {0.f, 0.f, 0.f};
+  if (X < g.Wu) {
+    float a[3][3][6];                                   // [channel][row Y-1..Y+1][column X-1..X+4]
+#pragma unroll
+    for (int c = 0; c < 3; ++c) tv_load_rows(g, u + size_t(c) * g.plane, Y, X, a[c]);
+    const int gy = g.row0 + Y, HuG = g.M + g.K - 1;
+    float T[3][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int x = X + i;
+      float dxc[3], dxl[3], dyc[3], dyu[3], pxc[3], pxl[3], pyc[3], pyu[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        dxc[c] = (x + 1 < g.Wu) ? a[c][1][i + 2] - a[c][1][i + 1] : 0.f;          // D_x at (y, x)
+        dxl[c] = (x >= 1 && x < g.Wu) ? a[c][1][i + 1] - a[c][1][i] : 0.f;         // D_x at (y, x-1)
+        dyc[c] = (gy + 1 < HuG) ? a[c][2][i + 1] - a[c][1][i + 1] : 0.f;           // D_y at (y, x)
+        dyu[c] = (gy >= 1) ? a[c][1][i + 1] - a[c][0][i + 1] : 0.f;                // D_y at (y-1, x)
+      }
+      ctv_field(dxc, eps, pxc);
+      ctv_field(dxl, eps, pxl);
+      ctv_field(dyc, eps, pyc);
+      ctv_field(dyu, eps, pyu);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float px_l = (x >= 1) ? pxl[c] : 0.f, py_u = (gy >= 1) ? pyu[c] : 0.f;
+        T[c][i] = -((pxc[c] - px_l) + (pyc[c] - py_u));
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const size_t off = size_t(c) * g.plane + size_t(Y) * g.pitch + X;
+      const float4 gv = *reinterpret_cast<const float4*>(gbuf + off);
+      const float gg[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (X + i < g.Wu) mG[c] = fmaxf(mG[c], fabsf(fmaf(lambd, gg[i], T[c][i])));
+      *reinterpret_cast<float4*>(tbuf + off) = make_float4(T[c][0], T[c][1], T[c][2], T[c][3]);
+    }
+  }
+  __shared__ float red[3][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float m = warp_max(mG[c]);
+    if (lane == 0) red[c][warp] = m;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float m = 0.f;
+    for (int w = 0; w < 8; ++w) m = fmaxf(m, red[threadIdx.x][w]);
+    atomicMax(&st->tvmax[slot][threadIdx.x], f2ord(m));
+  }
 }
 
 }  // namespace rltv

@@ -107,10 +107,12 @@ class Solver:
     @staticmethod
     def make_params(window, tau, iterations, step_factor, lambd, blind, correlation=False, mode="mm") -> nat.Params:
         top, bottom, left, right = (int(v) for v in window)
-        if mode not in ("mm", "mm_tv"):
-            raise ValueError("mode must be 'mm' (the reference's shipped arithmetic) or 'mm_tv' (TV term alive)")
+        modes = {"mm": nat.MODE_MM, "mm_tv": nat.MODE_MM_TV, "pam_ctv": nat.MODE_PAM_CTV}
+        if mode not in modes:
+            raise ValueError("mode must be 'mm' (the reference's shipped arithmetic), 'mm_tv' (its TV term alive) or "
+                             "'pam_ctv' (PAM step with the collaborative TV norm; unpinned extension)")
         return nat.Params(top, bottom, left, right, float(tau), int(iterations), float(step_factor), float(lambd),
-                          int(bool(blind)), int(bool(correlation)), nat.MODE_MM_TV if mode == "mm_tv" else nat.MODE_MM)
+                          int(bool(blind)), int(bool(correlation)), modes[mode])
 
     def download_image(self, image: np.ndarray) -> np.ndarray:
         """The blurry image as it is on the device (mode="mm_tv" denoises it in place, pyx:547-549)."""

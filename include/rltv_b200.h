@@ -59,6 +59,9 @@ typedef struct {
 } rltv_params_t;
 #define RLTV_MODE_MM 0
 #define RLTV_MODE_MM_TV 1
+#define RLTV_MODE_PAM_CTV 2      /* UNPINNED extension (no reference code exists for it, README.md:42-44, :113-117 only): PAM u-step
+                                  * u -= dt (lambda g - div p) with the collaborative l-inf,1,1 TV sub-gradient p over the three
+                                  * channels (definition: oracle/ctv_oracle.py); DoF blend and PSF step as in the reference */
 
 typedef struct {
   int32_t iterations_executed;      /* outer iterations run (pyx:656) */

@@ -449,3 +449,25 @@ def test_tv_alive_mode_against_oracle_larger_frame(dc):
     assert dc.last_stats["iterations"] == ref.iterations
     assert rel_l2(out, ref.out) <= TOL_IMAGE_REL_L2 and rel_l2(image, ref.image) <= TOL_IMAGE_REL_L2
     assert psf_l1(psf, ref.psf) <= TOL_PSF_L1
+
+
+@pytest.mark.parametrize("name,scale,iters", [("c3_blind_24mp_k15", 0.05, 3), ("c1_nonblind_512_g5", 0.3, 3)])
+def test_pam_collaborative_tv_mode_against_its_definition(dc, name, scale, iters):
+    """mode="pam_ctv" (k_ctv_grad + k_update_tv<PAM>): UNPINNED by the reference -- no PAM solver or collaborative norm
+    exists in the snapshot (README.md:42-44, :113-117 only).  Checked against the numpy statement of its definition
+    (oracle/ctv_oracle.py, oracle/rl_mm_oracle.py pam_ctv=True), and against the default mode (it must differ)."""
+    from image_cases_studies_b200 import synthetic
+    from oracle import rl_mm_oracle as orc
+    c = synthetic.make_case(name, seed=19, scale=scale, iterations=iters)
+    M, N = c.shape
+    image, u, psf = c.image.copy(), c.u0.copy(), c.psf0.copy()
+    out = dc.richardson_lucy_MM(image, u, psf, *c.window, c.tau, M, N, 3, c.MK, c.iterations, c.step_factor, c.lambd,
+                                blind=c.blind, mode="pam_ctv")
+    ref = orc.richardson_lucy_MM(c.image, c.u0, c.psf0, *c.window, c.tau, M, N, 3, c.MK, c.iterations, c.step_factor, c.lambd,
+                                 blind=c.blind, pam_ctv=True)
+    assert dc.last_stats["iterations"] == ref.iterations
+    assert rel_l2(out, ref.out) <= TOL_IMAGE_REL_L2 and psf_l1(psf, ref.psf) <= TOL_PSF_L1
+    assert np.array_equal(image, c.image)                      # this mode leaves the blurry image alone
+    mm = orc.richardson_lucy_MM(c.image, c.u0, c.psf0, *c.window, c.tau, M, N, 3, c.MK, c.iterations, c.step_factor, c.lambd,
+                                blind=c.blind)
+    assert rel_l2(mm.u, ref.u) > 1e-6

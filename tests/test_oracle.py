@@ -136,3 +136,19 @@ def test_tv_alive_oracle_against_patched_reference_fixtures(name):
     r0 = orc.richardson_lucy_MM(g["image"], g["u0"], g["psf0"], *g["window"], g["tau"], M, N, 3, K, g["iterations"],
                                 g["step_factor"], g["lambd"], blind=g["blind"])
     assert rel_l2(r0.u, g["ref_u"]) > 5e-4
+
+
+def test_collaborative_tv_definition_is_the_gradient_of_the_norm():
+    """oracle/ctv_oracle.py (UNPINNED: the reference has no collaborative norm, README only): T = -div p is the gradient
+    of TV_{inf,1,1}(u) = sum_pixels sum_d max_c |D_d u_c| (checked by a central difference along a random direction), and on
+    a grey image (three equal channels) only the first channel carries it."""
+    from oracle import ctv_oracle
+    rng = np.random.default_rng(2)
+    u = rng.random((18, 23, 3))
+    T = ctv_oracle.ctv_gradient(u, 1e-12)
+    v = rng.standard_normal(u.shape) * 1e-7
+    fd = (ctv_oracle.tv_inf11(u + v) - ctv_oracle.tv_inf11(u - v)) / 2
+    assert abs(fd - float((T * v).sum())) <= 1e-6 * abs(fd)
+    grey = np.repeat(rng.random((9, 11, 1)), 3, axis=2)
+    Tg = ctv_oracle.ctv_gradient(grey, 1e-3)
+    assert np.abs(Tg[..., 0]).max() > 0 and not Tg[..., 1:].any()
