@@ -146,12 +146,18 @@ __device__ __forceinline__ void fft128_core(float2* __restrict__ row, const floa
 #pragma unroll
   for (int j = 0; j < 16; ++j) x[j] = load(j);
   dft16<INV>(x);                                 // X'[q] = X[q] * w16^(-rot q)   (forward; conjugate for inverse)
+  // all 15 twiddles are fetched in one batch BEFORE the warp barrier (the compiler cannot move a load across it): fetched
+  // one by one after it, each multiplication waited for its own shared-memory round trip (ncu: short-scoreboard stalls on
+  // every FMUL2 of this loop, ~17 % of an FFT role's time)
+  const float2* twp = tw + (t + 8 * rot);        // w128^((t + 8 rot) q): w128^(t q) * w16^(+rot q) undoes the rotation
+  float2 wq[16];
+#pragma unroll
+  for (int q = 1; q < 16; ++q) wq[q] = twp[q * 32];
   __syncwarp(mask);                              // everyone's loads are done before anyone stores (in-place rows)
   row[t] = x[0];
-  const float2* twp = tw + (t + 8 * rot);        // w128^((t + 8 rot) q): w128^(t q) * w16^(+rot q) undoes the rotation
 #pragma unroll
   for (int q = 1; q < 16; ++q) {
-    float2 w = twp[q * 32];
+    float2 w = wq[q];
     if (INV) w.y = -w.y;
     row[9 * q + t] = cmulf(x[q], w);
   }

@@ -15,7 +15,10 @@ img = (0.1 + 0.8 * rng.random((M, N, 3), dtype=np.float32))
 psf = np.full((K, K, 3), 1.0 / (K * K), np.float32)
 s = Solver(M, N, K)
 s.upload(img, u, psf)
-names = {0: "all roles", 1: "no fwdFFT", 2: "no MAC", 4: "no IFFT/epi", 8 | 1: "no TMA+fwdFFT", 1 | 4 | 8: "MAC only", 2 | 4: "fwdFFT+TMA only", 1 | 2 | 8: "IFFT/epi only", 1 | 2 | 4 | 8: "loop + barriers only", 8: "no TMA (fwdFFT on stale data)"}
+# bits: 1 forward FFT, 2 E, 4 inverse FFT, 8 TMA loads, 16 G, 32 epilogue
+names = {0: "all roles", 63: "loop + barriers only", 61: "E only", 47: "G only", 45: "E + G only", 54: "fwdFFT + TMA only",
+         59: "IFFT only", 31: "EPI only", 18: "no E, no G", 32: "no EPI", 4 | 32: "no IFFT, no EPI", 1 | 8: "no TMA + fwdFFT",
+         2: "no E", 16: "no G"}
 for mask, name in names.items():
     nat.check(nat.lib.rltv_debug_chain_roles(mask))
     ts = []
