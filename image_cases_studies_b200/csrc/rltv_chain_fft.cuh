@@ -60,24 +60,22 @@ struct ChainCfg {
   static constexpr int ROLE = 128;
   static constexpr int T_E = 0, T_G = ROLE, T_IFFT = 2 * ROLE, T_FFT = 3 * ROLE, T_EPI = 4 * ROLE;
   static constexpr int THREADS = 6 * ROLE;
-  // registers per thread of every role (setmaxnreg; the kernel is launched with 80): 104 + 88 + 72 + 72 + 2 * 72 = 480 = 6 * 80
-  static constexpr int REG_E = 104, REG_G = 88, REG_FFT = 72, REG_EPI = 72;
+  // registers per thread of every role (setmaxnreg; the kernel is launched with 80): 112 + 96 + 72 + 72 + 2 * 64 = 480 = 6 * 80
+  static constexpr int REG_E = 112, REG_G = 96, REG_FFT = 72, REG_EPI = 64;
   static constexpr int DEPTH = 4;                           // the last role runs DEPTH time steps behind the first
   static constexpr int RB = 8;                              // MAC roles: rows per register block
   static constexpr int NB = S / RB;
   static constexpr int PCACHE = 24;                         // pieces of this CTA kept in shared memory
   static constexpr int T2 = 2 * P;                          // window rows a step needs from the previous ring block
-  static constexpr int WP = 65;                             // tap spectra are Hermitian: bins 0..64 are stored
   static constexpr int RING = 3;                            // blocks per ring: written / read with its predecessor / free
   static constexpr int U_BYTES = RING * S * FFT_PITCH * 8;  // U^ ring (forward FFT role writes, E reads)
   static constexpr int EC_BYTES = RING * S * FFT_N * 8;     // Err^ ring (E writes, G reads: thread = bin on both sides)
   static constexpr int GB_BYTES = RING * S * FFT_PITCH * 8; // G^ ring (G writes, IFFT transforms in place, EPI reads)
   static constexpr int IN_STAGE = 2 * S * INW * 4;          // one TMA stage: S real rows of each half
   static constexpr int IN_BYTES = 2 * IN_STAGE;
-  static constexpr int W_BYTES = ((2 * K * WP * 8) + 127) & ~127;
   static constexpr int TW_BYTES = FFT_TW_BYTES;
-  static constexpr int OFF_GB = U_BYTES, OFF_EC = OFF_GB + GB_BYTES, OFF_IN = OFF_EC + EC_BYTES, OFF_W = OFF_IN + IN_BYTES,
-                       OFF_TW = OFF_W + W_BYTES, OFF_BAR = OFF_TW + TW_BYTES;
+  static constexpr int OFF_GB = U_BYTES, OFF_EC = OFF_GB + GB_BYTES, OFF_IN = OFF_EC + EC_BYTES, OFF_TW = OFF_IN + IN_BYTES,
+                       OFF_BAR = OFF_TW + TW_BYTES;
   static constexpr int SMEM_BYTES = OFF_BAR + 64 + 128;
   static_assert(V % 4 == 0 && (K - 1 + DX) % 4 == 0, "float4 epilogue / aligned TMA box");
   static_assert(OFF_IN % 128 == 0 && IN_STAGE % 128 == 0, "TMA destination alignment");
@@ -152,13 +150,15 @@ __device__ __forceinline__ void set_maxnreg_dec() { asm volatile("setmaxnreg.dec
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // MAC over one block of R rows with a ROLLING register window:  acc[y] = sum_ky w[ky] * z[y + ky], where z[0 .. 2P) are
-// the last 2P window rows of the previous block (or the rows carried over from the previous step) and z[2P .. 2P + R)
-// the block's own rows, loaded here.  The caller moves the window down by R rows afterwards.  The loop over the blocks
-// of a step is NOT unrolled: straight-line code of a whole step (~30 KB) made the role instruction-fetch bound (ncu:
-// 'no instruction' was its top stall); one block body fits the L0 instruction cache.
+// the last 2P window rows of the previous block (or of the previous ring block) and z[2P .. 2P + R) the block's own
+// rows, loaded here.  The caller moves the window down by R rows afterwards.  The loop over the two blocks of a step is
+// NOT unrolled: with 24 warps in five different code regions per SM sub-partition the instruction caches are the scarce
+// resource (unrolled: every role slowed down, 0.54 -> 0.69 ms; straight-line code of a whole step made round 2's first
+// version instruction-fetch bound as well).  The taps sit in registers for a whole channel (conjugated there for the bins
+// above 64: real taps), which removes one shared-memory load and one select per tap and block from the loop.
 template <int K, int R, int CPITCH>
-__device__ __forceinline__ void chain_mac_block(float2 (&z)[R + K - 1], const float2* __restrict__ cur,
-                                                const float2* __restrict__ w, float sgn, float2 (&acc)[R]) {
+__device__ __forceinline__ void chain_mac_block(float2 (&z)[R + K - 1], const float2* __restrict__ cur, const float2 (&w)[K],
+                                                float2 (&acc)[R]) {
   using C = ChainCfg<K>;
 #pragma unroll
   for (int m = 0; m < R; ++m) z[C::T2 + m] = cur[m * CPITCH];
@@ -166,10 +166,8 @@ __device__ __forceinline__ void chain_mac_block(float2 (&z)[R + K - 1], const fl
   for (int y = 0; y < R; ++y) acc[y] = make_float2(0.f, 0.f);
 #pragma unroll
   for (int ky = 0; ky < K; ++ky) {
-    float2 wv = w[ky * C::WP];
-    wv.y *= sgn;                       // bins above 64 read the spectrum of bin 128 - k: conjugate (real taps)
 #pragma unroll
-    for (int y = 0; y < R; ++y) acc[y] = cfma(z[y + ky], wv, acc[y]);
+    for (int y = 0; y < R; ++y) acc[y] = cfma(z[y + ky], w[ky], acc[y]);
   }
 }
 
@@ -198,7 +196,6 @@ k_chain_fft(const __grid_constant__ CUtensorMap tm_u, Geom g, State* __restrict_
   float2* U = reinterpret_cast<float2*>(smem);
   float2* GB = reinterpret_cast<float2*>(smem + C::OFF_GB);
   float2* EC = reinterpret_cast<float2*>(smem + C::OFF_EC);
-  float2* WS = reinterpret_cast<float2*>(smem + C::OFF_W);          // [2][K][WP]: dir 0 scaled by 128, dir 1
   float2* tw = reinterpret_cast<float2*>(smem + C::OFF_TW);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);   // one mbarrier per TMA stage
   const int tid = threadIdx.x, lane = tid & 31;
@@ -322,7 +319,10 @@ k_chain_fft(const __grid_constant__ CUtensorMap tm_u, Geom g, State* __restrict_
     set_maxnreg_inc<C::REG_E>();
     const int mk = rt, kk = (mk <= 64) ? mk : FFT_N - mk;
     const float sgn = (mk > 64) ? -1.f : 1.f;
-    int cur_wc = -1;                                      // channel whose tap spectra are in shared memory
+    int cur_wc = -1;                                      // channel whose tap spectra are in the registers
+    float2 w[K];
+#pragma unroll
+    for (int ky = 0; ky < K; ++ky) w[ky] = make_float2(0.f, 0.f);
     float2 iv[RB];                                        // image spectra of the thread's next block (loaded one block ahead)
     {
       const float2* ip = Ipk + size_t(piece(p0).ipk_row0) * FFT_N + mk;
@@ -336,22 +336,17 @@ k_chain_fft(const __grid_constant__ CUtensorMap tm_u, Geom g, State* __restrict_
           const ChainPiece pc = piece(cur.p);
           if (pc.c != cur_wc) {
             // forward tap spectra of this channel, scaled by 128 (Err^ must be the unnormalised spectrum, like I^)
-            named_bar_sync(3, C::ROLE);
-            for (int i = rt; i < K * C::WP; i += C::ROLE) {
-              const int ky = i / C::WP, b = i - ky * C::WP;
-              float2 v = __ldg(wspec + (size_t(pc.c) * K + ky) * FFT_N + b);
-              v.x *= float(FFT_N);
-              v.y *= float(FFT_N);
-              WS[i] = v;
+#pragma unroll
+            for (int ky = 0; ky < K; ++ky) {
+              const float2 v = __ldg(wspec + (size_t(pc.c) * K + ky) * FFT_N + kk);
+              w[ky] = make_float2(v.x * float(FFT_N), v.y * (sgn * float(FFT_N)));
             }
-            named_bar_sync(3, C::ROLE);
             cur_wc = pc.c;
           }
           const int rb = s % C::RING, rp = (s + C::RING - 1) % C::RING;
           const float2* ucur = U + rb * C::S * FFT_PITCH + mk;
           const float2* uprev = U + (rp * C::S + C::S - C::T2) * FFT_PITCH + mk;
           float2* ecur = EC + rb * C::S * FFT_N + mk;
-          const float2* w0 = WS + kk;
           const float2* ip = Ipk + (size_t(pc.ipk_row0) + size_t(cur.j) * C::S) * FFT_N + mk;
           float2 z[RB + K - 1];
 #pragma unroll
@@ -359,7 +354,7 @@ k_chain_fft(const __grid_constant__ CUtensorMap tm_u, Geom g, State* __restrict_
 #pragma unroll 1
           for (int B = 0; B < C::NB; ++B) {
             float2 acc[RB];
-            chain_mac_block<K, RB, FFT_PITCH>(z, ucur + RB * B * FFT_PITCH, w0, sgn, acc);
+            chain_mac_block<K, RB, FFT_PITCH>(z, ucur + RB * B * FFT_PITCH, w, acc);
 #pragma unroll
             for (int y = 0; y < RB; ++y) ecur[(RB * B + y) * FFT_N] = make_float2(acc[y].x - iv[y].x, acc[y].y - iv[y].y);
             if (B + 1 < C::NB) {                           // image spectra of the next block: L2 hits, one block of MACs to land
@@ -388,18 +383,20 @@ k_chain_fft(const __grid_constant__ CUtensorMap tm_u, Geom g, State* __restrict_
     const int mk = rt, kk = (mk <= 64) ? mk : FFT_N - mk;
     const float sgn = (mk > 64) ? -1.f : 1.f;
     int cur_wc = -1;
+    float2 w[K];
+#pragma unroll
+    for (int ky = 0; ky < K; ++ky) w[ky] = make_float2(0.f, 0.f);
     for (int t = 0; t < nt; ++t) {
       if (t >= 2 && t - 2 < total) {
         if (!(skip & 16)) {
           const int s = t - 2;
           const ChainPiece pc = piece(cur.p);
           if (pc.c != cur_wc) {
-            named_bar_sync(4, C::ROLE);
-            for (int i = rt; i < K * C::WP; i += C::ROLE) {
-              const int ky = i / C::WP, b = i - ky * C::WP;
-              WS[K * C::WP + i] = __ldg(wspec + ((size_t(3) + pc.c) * K + ky) * FFT_N + b);
+#pragma unroll
+            for (int ky = 0; ky < K; ++ky) {
+              const float2 v = __ldg(wspec + ((size_t(3) + pc.c) * K + ky) * FFT_N + kk);
+              w[ky] = make_float2(v.x, v.y * sgn);
             }
-            named_bar_sync(4, C::ROLE);
             cur_wc = pc.c;
           }
           if (fix_on && needs_fix(pc, cur.j)) named_bar_sync(2, 2 * C::ROLE);   // the FFT role has masked this step's Err^
@@ -407,14 +404,13 @@ k_chain_fft(const __grid_constant__ CUtensorMap tm_u, Geom g, State* __restrict_
           const float2* ecur = EC + rb * C::S * FFT_N + mk;
           const float2* eprev = EC + (rp * C::S + C::S - C::T2) * FFT_N + mk;
           float2* gb = GB + rb * C::S * FFT_PITCH + mk;
-          const float2* w1 = WS + K * C::WP + kk;
           float2 z[RB + K - 1];
 #pragma unroll
           for (int m = 0; m < C::T2; ++m) z[m] = eprev[m * FFT_N];
 #pragma unroll 1
           for (int B = 0; B < C::NB; ++B) {
             float2 acc[RB];
-            chain_mac_block<K, RB, FFT_N>(z, ecur + RB * B * FFT_N, w1, sgn, acc);
+            chain_mac_block<K, RB, FFT_N>(z, ecur + RB * B * FFT_N, w, acc);
 #pragma unroll
             for (int y = 0; y < RB; ++y) gb[(RB * B + y) * FFT_PITCH] = acc[y];
 #pragma unroll
@@ -442,78 +438,88 @@ k_chain_fft(const __grid_constant__ CUtensorMap tm_u, Geom g, State* __restrict_
     const int re = tid - C::T_EPI, zr = re >> 4, tt = re & 15;
     constexpr int NQ = (C::V / 4 + 15) / 16;              // float4 columns per thread
     float mu = -INFINITY, mG = 0.f;                       // statistics of the current piece's channel
+    // one pixel of a g row: the statistic max|lambda g + (u - ut)/2| (pyx:519) and max(u) (pyx:524)
+    auto px = [&](float o, float uu, float tv) {
+      mG = fmaxf(mG, fabsf(fmaf(lambd, o, 0.5f * (uu - tv))));
+      mu = fmaxf(mu, uu);
+    };
     for (int t = 0; t < nt; ++t) {
       if (t >= 4 && t - 4 < total) {
         const ChainPiece pc = piece(cur.p);
         if (!(skip & 32)) {
           const int rel = cur.j * C::S - 4 * C::P + zr;                // g row of the first half, relative to the piece
-          const int ya = pc.ya + rel, yb = ya + pc.L;
           const bool va = rel >= 0 && rel < pc.L, vb = rel >= 0 && rel < pc.Lb;
           const int xs = C::V * pc.s;
-          const size_t offa = size_t(pc.c) * g.plane + size_t(va ? ya : 0) * g.pitch + xs;
-          const size_t offb = size_t(pc.c) * g.plane + size_t(vb ? yb : 0) * g.pitch + xs;
+          const size_t offa = size_t(pc.c) * g.plane + size_t(va ? pc.ya + rel : 0) * g.pitch + xs;
+          const size_t offb = size_t(pc.c) * g.plane + size_t(vb ? pc.ya + rel + pc.L : 0) * g.pitch + xs;
+          const float* pua = ug + offa;
+          const float* pub = ug + offb;
+          const float* pta = (ut_is_u ? ug : utg) + offa;
+          const float* ptb = (ut_is_u ? ug : utg) + offb;
           // all operand loads first (clamped addresses instead of branches: with a branch per load the compiler
           // serialises the round trips); the rows were brought into L2 one time step ago
           float4 ua[NQ], ta[NQ], ub[NQ], tb[NQ];
 #pragma unroll
           for (int q = 0; q < NQ; ++q) {
             const int x4 = 4 * (tt + 16 * q);
-            const bool ok = x4 < C::V && xs + x4 < g.pitch;
-            const int xc = ok ? x4 : 0;
-            ua[q] = __ldg(reinterpret_cast<const float4*>(ug + offa + xc));
-            ub[q] = __ldg(reinterpret_cast<const float4*>(ug + offb + xc));
-            if (!ut_is_u) {
-              ta[q] = __ldg(reinterpret_cast<const float4*>(utg + offa + xc));
-              tb[q] = __ldg(reinterpret_cast<const float4*>(utg + offb + xc));
-            } else {
-              ta[q] = ua[q];
-              tb[q] = ub[q];
-            }
+            const int xc = (x4 < C::V && xs + x4 < g.pitch) ? x4 : 0;
+            ua[q] = __ldg(reinterpret_cast<const float4*>(pua + xc));
+            ub[q] = __ldg(reinterpret_cast<const float4*>(pub + xc));
+            ta[q] = __ldg(reinterpret_cast<const float4*>(pta + xc));
+            tb[q] = __ldg(reinterpret_cast<const float4*>(ptb + xc));
           }
-          // the rows of the NEXT step into L2 (a whole time step ahead of their use)
+          // the rows of the NEXT step into L2 (a whole time step ahead of their use): one line address per thread --
+          // (array, half, line) -- the 16-byte aligned row of V floats touches four lines of 128 B, or a fifth
           if (t - 3 < total) {
             ChainCursor nx = cur;
             advance(nx);
             const ChainPiece pn = piece(nx.p);
             const int reln = nx.j * C::S - 4 * C::P + zr;
-            const bool vna = reln >= 0 && reln < pn.L, vnb = reln >= 0 && reln < pn.Lb;
+            const int arr = tt & 1, part = (tt >> 1) & 1, ln = tt >> 2;
+            const bool v = reln >= 0 && reln < (part ? pn.Lb : pn.L);
             const int xn = C::V * pn.s;
-            // 2 arrays x 2 rows x (V * 4 bytes = up to 4 lines of 128 B, unaligned: 5) = 20 line addresses over 16 threads
-            for (int i = tt; i < 20; i += 16) {
-              const int arr = i & 1, part = (i >> 1) & 1, ln = i >> 2;
-              const bool v = part ? vnb : vna;
-              const int y = pn.ya + reln + (part ? pn.L : 0);
-              int x = xn + 32 * ln;
-              if (x > xn + C::V - 4) x = xn + C::V - 4;
-              if (v && x < g.pitch && !(arr && ut_is_u))
-                prefetch_l2((arr ? utg : ug) + size_t(pn.c) * g.plane + size_t(y) * g.pitch + x);
+            if (v && !(arr && ut_is_u)) {
+              const float* rowp = (arr ? utg : ug) + size_t(pn.c) * g.plane + size_t(pn.ya + reln + (part ? pn.L : 0)) * g.pitch + xn;
+              if (xn + 32 * ln < g.pitch) prefetch_l2(rowp + 32 * ln);
+              if (ln == 0 && xn + C::V - 4 < g.pitch) prefetch_l2(rowp + C::V - 4);
             }
           }
-          const float2* row = GB + (((t - 4) % C::RING) * C::S + zr) * FFT_PITCH;
+          const float2* row = GB + (((t - 4) % C::RING) * C::S + zr) * FFT_PITCH + (K - 1);
+          const bool full = xs + C::V <= g.Wu;                         // the segment lies inside the row: no column checks
 #pragma unroll
           for (int q = 0; q < NQ; ++q) {
             const int x4 = 4 * (tt + 16 * q);
-            const bool ok = x4 < C::V && xs + x4 < g.pitch;
-            if (!ok) continue;
-            const int Xm = xs + x4;
-            const bool c0 = Xm < g.Wu, c1 = Xm + 1 < g.Wu, c2 = Xm + 2 < g.Wu, c3 = Xm + 3 < g.Wu;
-            const float4 z01 = lds128(row + (K - 1) + x4);            // (re0, im0, re1, im1)
-            const float4 z23 = lds128(row + (K - 1) + x4 + 2);
-            if (va) {
-              const float4 o = make_float4(c0 ? z01.x : 0.f, c1 ? z01.z : 0.f, c2 ? z23.x : 0.f, c3 ? z23.z : 0.f);
-              if (c0) { mG = fmaxf(mG, fabsf(fmaf(lambd, o.x, 0.5f * (ua[q].x - ta[q].x)))); mu = fmaxf(mu, ua[q].x); }   // pyx:519, :524
-              if (c1) { mG = fmaxf(mG, fabsf(fmaf(lambd, o.y, 0.5f * (ua[q].y - ta[q].y)))); mu = fmaxf(mu, ua[q].y); }
-              if (c2) { mG = fmaxf(mG, fabsf(fmaf(lambd, o.z, 0.5f * (ua[q].z - ta[q].z)))); mu = fmaxf(mu, ua[q].z); }
-              if (c3) { mG = fmaxf(mG, fabsf(fmaf(lambd, o.w, 0.5f * (ua[q].w - ta[q].w)))); mu = fmaxf(mu, ua[q].w); }
-              *reinterpret_cast<float4*>(gout + offa + x4) = o;
-            }
-            if (vb) {
-              const float4 o = make_float4(c0 ? z01.y : 0.f, c1 ? z01.w : 0.f, c2 ? z23.y : 0.f, c3 ? z23.w : 0.f);
-              if (c0) { mG = fmaxf(mG, fabsf(fmaf(lambd, o.x, 0.5f * (ub[q].x - tb[q].x)))); mu = fmaxf(mu, ub[q].x); }
-              if (c1) { mG = fmaxf(mG, fabsf(fmaf(lambd, o.y, 0.5f * (ub[q].y - tb[q].y)))); mu = fmaxf(mu, ub[q].y); }
-              if (c2) { mG = fmaxf(mG, fabsf(fmaf(lambd, o.z, 0.5f * (ub[q].z - tb[q].z)))); mu = fmaxf(mu, ub[q].z); }
-              if (c3) { mG = fmaxf(mG, fabsf(fmaf(lambd, o.w, 0.5f * (ub[q].w - tb[q].w)))); mu = fmaxf(mu, ub[q].w); }
-              *reinterpret_cast<float4*>(gout + offb + x4) = o;
+            if (x4 >= C::V || xs + x4 >= g.pitch) continue;
+            const float4 z01 = lds128(row + x4);                       // (re0, im0, re1, im1)
+            const float4 z23 = lds128(row + x4 + 2);
+            if (full) {
+              if (va) {
+                px(z01.x, ua[q].x, ta[q].x); px(z01.z, ua[q].y, ta[q].y); px(z23.x, ua[q].z, ta[q].z); px(z23.z, ua[q].w, ta[q].w);
+                *reinterpret_cast<float4*>(gout + offa + x4) = make_float4(z01.x, z01.z, z23.x, z23.z);
+              }
+              if (vb) {
+                px(z01.y, ub[q].x, tb[q].x); px(z01.w, ub[q].y, tb[q].y); px(z23.y, ub[q].z, tb[q].z); px(z23.w, ub[q].w, tb[q].w);
+                *reinterpret_cast<float4*>(gout + offb + x4) = make_float4(z01.y, z01.w, z23.y, z23.w);
+              }
+            } else {
+              const int nv = g.Wu - (xs + x4);                         // columns of this float4 inside the row (may be <= 0)
+              const bool c0 = nv > 0, c1 = nv > 1, c2 = nv > 2, c3 = nv > 3;
+              if (va) {
+                const float4 o = make_float4(c0 ? z01.x : 0.f, c1 ? z01.z : 0.f, c2 ? z23.x : 0.f, c3 ? z23.z : 0.f);
+                if (c0) px(o.x, ua[q].x, ta[q].x);
+                if (c1) px(o.y, ua[q].y, ta[q].y);
+                if (c2) px(o.z, ua[q].z, ta[q].z);
+                if (c3) px(o.w, ua[q].w, ta[q].w);
+                *reinterpret_cast<float4*>(gout + offa + x4) = o;
+              }
+              if (vb) {
+                const float4 o = make_float4(c0 ? z01.y : 0.f, c1 ? z01.w : 0.f, c2 ? z23.y : 0.f, c3 ? z23.w : 0.f);
+                if (c0) px(o.x, ub[q].x, tb[q].x);
+                if (c1) px(o.y, ub[q].y, tb[q].y);
+                if (c2) px(o.z, ub[q].z, tb[q].z);
+                if (c3) px(o.w, ub[q].w, tb[q].w);
+                *reinterpret_cast<float4*>(gout + offb + x4) = o;
+              }
             }
           }
           // end of a piece: flush the statistics of its channel
