@@ -271,7 +271,7 @@ k_chain_fft(const __grid_constant__ CUtensorMap tm_u, Geom g, State* __restrict_
           const int rb = (t - 2) % C::RING;
           float2* scratch = GB + (rb * C::S + zr) * FFT_PITCH;       // G^ block of that step: not written yet
           float2* erow = EC + (rb * C::S + zr) * FFT_N;
-          fft128_core<true>(scratch, tw, tt, [&](int j) { return erow[tt + 8 * j]; }, 0xffffffffu, 0);
+          fft128_core<true, true>(scratch, tw, tt, [&](int j) { return erow[tt + 8 * j]; }, 0xffffffffu, 0);
           __syncwarp();
           const int ea = pc.ya + cfix.j * C::S - 3 * C::P + zr, eb = ea + pc.L;
           const bool rowa = ea >= imgLo && ea < imgHi, rowb = eb >= imgLo && eb < imgHi;
@@ -286,7 +286,7 @@ k_chain_fft(const __grid_constant__ CUtensorMap tm_u, Geom g, State* __restrict_
             scratch[n] = v;
           }
           __syncwarp();
-          fft128_core<false>(scratch, tw, tt, [&](int j) { return scratch[tt + 8 * j]; }, 0xffffffffu, 0);
+          fft128_core<false, true>(scratch, tw, tt, [&](int j) { return scratch[tt + 8 * j]; }, 0xffffffffu, 0);
           __syncwarp();
           for (int n = tt; n < FFT_N; n += 8) erow[n] = scratch[n];
           __threadfence_block();
@@ -303,7 +303,7 @@ k_chain_fft(const __grid_constant__ CUtensorMap tm_u, Geom g, State* __restrict_
           if (!(skip & 8)) mbar_wait(bar + (t & 1), (t >> 1) & 1);
           const float* ra = reinterpret_cast<const float*>(smem + C::OFF_IN + (t & 1) * C::IN_STAGE) + zr * C::INW + C::DX + tt;
           float2* dst = U + ((t % C::RING) * C::S + zr) * FFT_PITCH;
-          fft128_core<false>(dst, tw, tt, [&](int j) { return make_float2(ra[8 * j], ra[C::S * C::INW + 8 * j]); }, 0xffffffffu, 0);
+          fft128_core<false, true>(dst, tw, tt, [&](int j) { return make_float2(ra[8 * j], ra[C::S * C::INW + 8 * j]); }, 0xffffffffu, 0);
         }
         advance(cur);
       }
@@ -428,7 +428,7 @@ k_chain_fft(const __grid_constant__ CUtensorMap tm_u, Geom g, State* __restrict_
     for (int t = 0; t < nt; ++t) {
       if (t >= 3 && t - 3 < total && !(skip & 4)) {
         float2* row = GB + (((t - 3) % C::RING) * C::S + zr) * FFT_PITCH;
-        fft128_core<true>(row, tw, tt, [&](int j) { return row[tt + 8 * j]; }, 0xffffffffu, 0);
+        fft128_core<true, true>(row, tw, tt, [&](int j) { return row[tt + 8 * j]; }, 0xffffffffu, 0);
       }
       step_barrier();
     }

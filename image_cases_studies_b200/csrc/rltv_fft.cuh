@@ -139,25 +139,28 @@ __device__ __forceinline__ void fft_fill_twiddles(float2* tw) {
 // `rot` (0..3) rotates the order in which the 16 stride-8 samples are fetched (x'[j] = x[(j + rot) mod 16]); by the
 // shift theorem that only changes the pass-A twiddle index.  Callers whose four rows per warp would otherwise read
 // the same banks of a dense 512-byte-pitch source use different `rot` per row; everybody else passes 0.
-template <bool INV, typename Load>
+template <bool INV, bool BATCH = false, typename Load>
 __device__ __forceinline__ void fft128_core(float2* __restrict__ row, const float2* __restrict__ tw, int t, Load load,
                                             unsigned mask, int rot) {
   float2 x[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) x[j] = load(j);
   dft16<INV>(x);                                 // X'[q] = X[q] * w16^(-rot q)   (forward; conjugate for inverse)
-  // all 15 twiddles are fetched in one batch BEFORE the warp barrier (the compiler cannot move a load across it): fetched
-  // one by one after it, each multiplication waited for its own shared-memory round trip (ncu: short-scoreboard stalls on
-  // every FMUL2 of this loop, ~17 % of an FFT role's time)
+  // BATCH: all 15 twiddles are fetched in one batch BEFORE the warp barrier (the compiler cannot move a load across it):
+  // fetched one by one after it, each multiplication waits for its own shared-memory round trip (ncu: short-scoreboard
+  // stalls on every FMUL2 of this loop, ~17 % of an FFT role's time in the chain kernel).  Costs 30 registers across the
+  // barrier, which the phase-structured tile kernels (many warps in the same phase, registers at their cap) do not have.
   const float2* twp = tw + (t + 8 * rot);        // w128^((t + 8 rot) q): w128^(t q) * w16^(+rot q) undoes the rotation
-  float2 wq[16];
+  float2 wq[BATCH ? 16 : 1];
+  if constexpr (BATCH) {
 #pragma unroll
-  for (int q = 1; q < 16; ++q) wq[q] = twp[q * 32];
+    for (int q = 1; q < 16; ++q) wq[q] = twp[q * 32];
+  }
   __syncwarp(mask);                              // everyone's loads are done before anyone stores (in-place rows)
   row[t] = x[0];
 #pragma unroll
   for (int q = 1; q < 16; ++q) {
-    float2 w = wq[q];
+    float2 w = BATCH ? wq[q] : twp[q * 32];
     if (INV) w.y = -w.y;
     row[9 * q + t] = cmulf(x[q], w);
   }
@@ -180,11 +183,11 @@ __device__ __forceinline__ void fft128_core(float2* __restrict__ row, const floa
 }
 
 // Generic form: `load(n)` returns input element n in [0, 128).
-template <bool INV, typename Load>
+template <bool INV, bool BATCH = false, typename Load>
 __device__ __forceinline__ void fft128_row(float2* __restrict__ row, const float2* __restrict__ tw, int t, Load load,
                                            unsigned mask = 0xffffffffu, int rot = 0) {
   const int base = t + 8 * rot;
-  fft128_core<INV>(row, tw, t, [&](int j) { return load((base + 8 * j) & (FFT_N - 1)); }, mask, rot);
+  fft128_core<INV, BATCH>(row, tw, t, [&](int j) { return load((base + 8 * j) & (FFT_N - 1)); }, mask, rot);
 }
 
 // Debug / test kernel: transforms `nrows` rows of 128 complex values (global, packed) one CTA per 16 rows.

@@ -334,7 +334,10 @@ struct GradkFftCfg {
   static constexpr int P4 = (P + 3) & ~3;
   static constexpr int TWO = FftCfg<K>::TWO;
   static constexpr int HB = (K <= 17) ? 40 : (K <= 31 ? 32 : 24);   // shared memory: (HB + K - 1) spectra rows of u
-  static constexpr int THREADS = (K <= 17) ? 512 : 256;   // large K: 2K complex accumulators + a K-deep window per thread
+#ifndef RLTV_GRADK_THREADS
+#define RLTV_GRADK_THREADS 512   // (640 threads, five row chunks: 0.58 vs 0.54 ms at 24 MP)
+#endif
+  static constexpr int THREADS = (K <= 17) ? RLTV_GRADK_THREADS : 256;   // large K: 2K complex accumulators + a K-deep window per thread
   static constexpr int TROWS = 2 * HB;
   static constexpr int U_ROWS = TROWS + K - 1;      // real u rows per tile
   static constexpr int ZU_ROWS = HB + K - 1;
@@ -666,13 +669,15 @@ k_gradk_fft_finish(State* __restrict__ st, const float2* __restrict__ part, int 
   }
   if (cp.nranks > 1 || fold) {
     __shared__ int s_last;
-    __threadfence_system();
+    // the sums cross GPUs only with row bands; on one GPU a device-scope fence orders them before the ticket (the
+    // system-scope fence was 36 % of this kernel's stall samples)
+    if (cp.nranks > 1) __threadfence_system(); else __threadfence();
     __syncthreads();
     if (tid == 0) {
       const int last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
       if (last) {
         *ticket = 0u;
-        __threadfence_system();
+        if (cp.nranks > 1) __threadfence_system(); else __threadfence();
         if (cp.nranks > 1) {
           for (int rr = 0; rr < cp.nranks; ++rr) *reinterpret_cast<volatile int*>(&cp.peer[rr]->gk_flag[par][cp.rank]) = seq;
           __threadfence_system();
