@@ -434,12 +434,13 @@ def main():
     fam_tot = {f: t for f, (t, n) in prof.items()}
     tot = sum(fam_tot.values()) or 1.0
     dom = max(("conv_fwd", "conv_adj", "update", "gradk"), key=lambda f: fam_tot.get(f, 0.0))
-    conv_mode = os.environ.get("RLTV_CONV", "fft" if K >= 11 else "direct")
+    # default kernel family of the library (rltv_api.cu): row-FFT / chain kernels for K >= 11, and for K = 9 on megapixel frames
+    conv_mode = os.environ.get("RLTV_CONV", "fft" if (K >= 11 or (K == 9 and M * N >= (1 << 20))) else "direct")
     fused_residual = case.blind and conv_mode == "fft" and K <= 17 and os.environ.get("RLTV_FUSE", "1") != "0"
     fam_bytes = dict(FAMILY_BYTES_PER_PX)
-    # 11 <= K <= 17: forward blur, residual and adjoint are ONE launch (k_chain_fft), timed under the conv_adj family:
+    # chain kernel (9 <= K <= 17 on the row-FFT path): forward blur, residual and adjoint are ONE launch (k_chain_fft), timed under the conv_adj family:
     # reads u, ut, image (as packed spectra), writes g
-    chain = conv_mode == "fft" and 11 <= K <= 17 and os.environ.get("RLTV_CHAIN", "1") != "0" and (world == 1 or args.comm == "fused")
+    chain = conv_mode == "fft" and 9 <= K <= 17 and os.environ.get("RLTV_CHAIN", "1") != "0" and (world == 1 or args.comm == "fused")
     if chain:
         fam_bytes["conv_adj"] = 48.0
     if fused_residual:
@@ -471,7 +472,7 @@ def main():
                          "direct_equivalent_tflops": flops_launch / (dom_ms * 1e-3) / 1e12 if dom_ms else 0.0,
                          "peak_tflops": fpk, "peak_source": fpk_src,
                          "direct_equivalent_over_peak": (flops_launch / (dom_ms * 1e-3) / 1e12) / fpk if dom_ms else 0.0,
-                         "algorithm": "row-FFT hybrid" if 11 <= K <= 17 and os.environ.get("RLTV_CONV") != "direct" else "direct stencil"},
+                         "algorithm": "row-FFT hybrid" if conv_mode == "fft" else "direct stencil"},
                 "step": {"algorithmic_bytes": step_bytes, "achieved_gbs": step_bytes / (ms_step * 1e-3) / 1e9,
                          "frac_of_hbm_all_gpus": step_bytes / (ms_step * 1e-3) / 1e9 / (hbm_peak * world)},
                 "family_ms_per_launch": fam_ms, "family_share": {f: t / tot for f, t in fam_tot.items()}}

@@ -510,7 +510,9 @@ int chain_setup_t(rltv_ctx* c) {
     // balanced split of the weighted row sequence (strip-major) into one contiguous range per CTA; a border strip
     // (masking path every step) counts 1.7x
     std::vector<double> wsum(nstrips + 1, 0.0);
-    for (int i = 0; i < nstrips; ++i) wsum[i + 1] = wsum[i] + (xfix(i % nseg) ? 1.7 : 1.0) * R;
+    double fixw = 1.7;
+    if (const char* e = getenv("RLTV_CHAIN_FIXW")) fixw = atof(e);
+    for (int i = 0; i < nstrips; ++i) wsum[i + 1] = wsum[i] + (xfix(i % nseg) ? fixw : 1.0) * R;
     const double total = wsum[nstrips];
     auto pos_of = [&](double w, int& strip, int& row) {      // inverse of the cumulative weight
       strip = 0;
@@ -969,14 +971,16 @@ int rltv_create_band(rltv_ctx** out, int32_t device, int32_t M, int32_t N, int32
   {
     // Row-FFT hybrid stencils (csrc/rltv_stencil_fft.cuh) for the FP32-bound sizes; RLTV_CONV=direct|fft overrides
     const char* e = getenv("RLTV_CONV");
-    c->use_fft = (MK >= 11);
+    // K = 9: the chain kernel + fused PSF gradient win on megapixel frames since the five-role chain kernel (C2, 2 MP:
+    // 13.2 vs 12.2 GPix*iter/s); small crops keep the direct stencils (no pipeline fill, no piece priming)
+    c->use_fft = (MK >= 11) || (MK == 9 && size_t(M) * N >= (size_t(1) << 20));
     if (e && !strcmp(e, "direct") && MK <= RLTV_MAX_DIRECT_MK) c->use_fft = false;
     if (e && !strcmp(e, "fft") && MK >= 9) c->use_fft = true;
     c->use_fft_gradk = c->use_fft;
     c->fuse_residual = c->use_fft_gradk && MK <= 17;             // GradkFftCfg<K>::CAN_FUSE
     if (const char* e = getenv("RLTV_FUSE")) c->fuse_residual = c->fuse_residual && atoi(e) != 0;
     // spectral chain kernel: default for the sizes it exists for; RLTV_CHAIN=0 keeps the two-kernel gradient path
-    c->use_chain = c->use_fft && MK >= 9 && MK <= 17;   // (K = 9 only with RLTV_CONV=fft: the direct kernels win there, 12.6 vs 11.7 GPix*iter/s on C2)
+    c->use_chain = c->use_fft && MK >= 9 && MK <= 17;
     if (const char* e = getenv("RLTV_CHAIN")) c->use_chain = c->use_chain && atoi(e) != 0;
   }
   {
