@@ -298,11 +298,14 @@ int launch_conv_fwd_rows_t(rltv_ctx* c, int y0, int y1) {
   }
 }
 
+int launch_conv_fwd(rltv_ctx* c);
 int launch_conv_fwd_window(rltv_ctx* c) {
   int y0 = c->wg.top + c->g.P - c->g.row0, y1 = y0 + c->wg.h;
   if (y0 < 0) y0 = 0;
   if (y1 > c->g.Hu) y1 = c->g.Hu;
   switch (c->g.K) {
+    case 5:
+    case 7: return launch_conv_fwd(c);       // direct forward stencil (whole frame; the row-FFT tile kernels start at K = 9)
     case 9: return launch_conv_fwd_rows_t<9>(c, y0, y1);
     case 11: return launch_conv_fwd_rows_t<11>(c, y0, y1);
     case 13: return launch_conv_fwd_rows_t<13>(c, y0, y1);
@@ -313,7 +316,7 @@ int launch_conv_fwd_window(rltv_ctx* c) {
 }
 
 int launch_psf_spectrum(rltv_ctx* c) {
-  if (!c->use_fft) return RLTV_OK;
+  if (!c->use_fft && !c->use_chain) return RLTV_OK;
   ProfScope p(c, F_PSF);
   k_psf_spectrum<<<dim3(c->g.K, 3, 2), FFT_N, 0, c->stream>>>(c->st, c->psf, c->g.K, c->wspec);
   return RLTV_OK;
@@ -501,7 +504,7 @@ int launch_update(rltv_ctx* c) {
 // ---- spectral chain kernel: work partition, image spectra, launch -------------------------------------------
 template <int K>
 int chain_setup_t(rltv_ctx* c) {
-  if constexpr (K >= 9 && K <= 17) {
+  if constexpr (K >= 5 && K <= 17) {
     using C = ChainCfg<K>;
     const Geom& g = c->g;
     const int nseg = chain_nseg(g.Wu, C::V), nstrips = 3 * nseg, G = c->num_sms;
@@ -565,26 +568,26 @@ int chain_setup_t(rltv_ctx* c) {
     c->chain_ipk_valid = false;
     return RLTV_OK;
   } else {
-    return fail(RLTV_ERR_ARG, "the chain kernel exists for 9 <= MK <= 17");
+    return fail(RLTV_ERR_ARG, "the chain kernel exists for 5 <= MK <= 17");
   }
 }
 
 template <int K>
 int chain_image_spectra_t(rltv_ctx* c) {
-  if constexpr (K >= 9 && K <= 17) {
+  if constexpr (K >= 5 && K <= 17) {
     k_chain_image_spectra<K><<<dim3(8, c->chain_npieces < 2048 ? c->chain_npieces : 2048), 256, 0, c->stream>>>(
         c->g, c->img, c->chain_pieces, c->chain_npieces, c->chain_ipk);
     c->launches++;
     c->chain_ipk_valid = true;
     return RLTV_OK;
   } else {
-    return fail(RLTV_ERR_ARG, "the chain kernel exists for 9 <= MK <= 17");
+    return fail(RLTV_ERR_ARG, "the chain kernel exists for 5 <= MK <= 17");
   }
 }
 
 template <int K>
 int launch_chain_t(rltv_ctx* c, float lambd) {
-  if constexpr (K >= 9 && K <= 17) {
+  if constexpr (K >= 5 && K <= 17) {
     using C = ChainCfg<K>;
     if (c->peers.nranks > 1) c->max_seq += 1;
     ProfScope p(c, F_CONV_ADJ);
@@ -593,19 +596,21 @@ int launch_chain_t(rltv_ctx* c, float lambd) {
         c->inner_count & 1, c->inner_in_outer == 0 ? 1 : 0, c->peers, c->max_seq, c->counters + 1);
     return RLTV_OK;
   } else {
-    return fail(RLTV_ERR_ARG, "the chain kernel exists for 9 <= MK <= 17");
+    return fail(RLTV_ERR_ARG, "the chain kernel exists for 5 <= MK <= 17");
   }
 }
 
 #define RLTV_CHAIN_DISPATCH(FN, ...)                                   \
   switch (c->g.K) {                                                    \
+    case 5: return FN<5>(__VA_ARGS__);                                 \
+    case 7: return FN<7>(__VA_ARGS__);                                 \
     case 9: return FN<9>(__VA_ARGS__);                                 \
     case 11: return FN<11>(__VA_ARGS__);                               \
     case 13: return FN<13>(__VA_ARGS__);                               \
     case 15: return FN<15>(__VA_ARGS__);                               \
     case 17: return FN<17>(__VA_ARGS__);                               \
   }                                                                    \
-  return fail(RLTV_ERR_ARG, "the chain kernel exists for MK = 11..17");
+  return fail(RLTV_ERR_ARG, "the chain kernel exists for MK = 5..17");
 int chain_setup(rltv_ctx* c) { RLTV_CHAIN_DISPATCH(chain_setup_t, c) }
 int chain_image_spectra(rltv_ctx* c) { RLTV_CHAIN_DISPATCH(chain_image_spectra_t, c) }
 int launch_chain(rltv_ctx* c, float lambd) { RLTV_CHAIN_DISPATCH(launch_chain_t, c, lambd) }
@@ -973,7 +978,9 @@ int rltv_create_band(rltv_ctx** out, int32_t device, int32_t M, int32_t N, int32
     const char* e = getenv("RLTV_CONV");
     // K = 9: the chain kernel + fused PSF gradient win on megapixel frames since the five-role chain kernel (C2, 2 MP:
     // 13.2 vs 12.2 GPix*iter/s); small crops keep the direct stencils (no pipeline fill, no piece priming)
-    c->use_fft = (MK >= 11) || (MK == 9 && size_t(M) * N >= (size_t(1) << 20));
+    size_t minpix = size_t(1) << 20;                             // RLTV_CHAIN_MINPIX: tests drive the small-K chain path on small frames
+    if (const char* mp = getenv("RLTV_CHAIN_MINPIX")) minpix = size_t(atoll(mp));
+    c->use_fft = (MK >= 11) || (MK == 9 && size_t(M) * N >= minpix);
     if (e && !strcmp(e, "direct") && MK <= RLTV_MAX_DIRECT_MK) c->use_fft = false;
     if (e && !strcmp(e, "fft") && MK >= 9) c->use_fft = true;
     c->use_fft_gradk = c->use_fft;
@@ -981,6 +988,9 @@ int rltv_create_band(rltv_ctx** out, int32_t device, int32_t M, int32_t N, int32
     if (const char* e = getenv("RLTV_FUSE")) c->fuse_residual = c->fuse_residual && atoi(e) != 0;
     // spectral chain kernel: default for the sizes it exists for; RLTV_CHAIN=0 keeps the two-kernel gradient path
     c->use_chain = c->use_fft && MK >= 9 && MK <= 17;
+    // K = 5, 7 on megapixel frames: the chain kernel does the gradient (it is bound by its FFT / epilogue roles there, not by
+    // the 2K complex MACs), everything else stays on the direct stencils (the row-FFT tile kernels start at K = 9)
+    if ((MK == 5 || MK == 7) && size_t(M) * N >= minpix && !(e && !strcmp(e, "direct"))) c->use_chain = true;
     if (const char* e = getenv("RLTV_CHAIN")) c->use_chain = c->use_chain && atoi(e) != 0;
   }
   {
@@ -1056,7 +1066,7 @@ int rltv_upload_band(rltv_ctx* c, const float* image, size_t image_rs, int32_t i
     k_psf_pack<<<(3 * KK2 + 255) / 256, 256, 0, c->stream>>>(c->psf_hwc, c->psf, KK2, 1);
     CU(cudaMemcpyAsync(c->psf_caller, c->psf, size_t(3) * KK2 * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
     c->launches++;
-    if (c->use_fft) {
+    if (c->use_fft || c->use_chain) {
       CU(cudaMemsetAsync(c->st, 0, sizeof(int), c->stream));   // a stop flag left by an earlier solve must not skip this
       int rc2 = launch_psf_spectrum(c);
       if (rc2) return rc2;

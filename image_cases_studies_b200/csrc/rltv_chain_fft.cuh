@@ -50,7 +50,7 @@ struct ChainPiece {
 
 template <int K>
 struct ChainCfg {
-  static_assert(K >= 9 && K <= 17, "two chained circular convolutions on 128-sample segments");
+  static_assert(K >= 5 && K <= 17, "two chained circular convolutions on 128-sample segments");
   static constexpr int P = K / 2;
   static constexpr int V = FFT_N - 2 * (K - 1);             // valid g columns per segment
   static constexpr int DX = (4 - ((K - 1) & 3)) & 3;        // FFT sample n sits at TMA box column n + DX (16-byte aligned box start)

@@ -367,15 +367,16 @@ def test_row_fft_solver_against_oracle(dc, monkeypatch):
         dc.clear_cache()
 
 
-@pytest.mark.parametrize("K", [11, 13, 15, 17])
+@pytest.mark.parametrize("K", [5, 7, 9, 11, 13, 15, 17])
 @pytest.mark.parametrize("shape", [(5, 9), (61, 97), (100, 100), (203, 251), (331, 420)])
-def test_chain_kernel_against_oracle(K, shape):
+def test_chain_kernel_against_oracle(K, shape, monkeypatch):
     """k_chain_fft (csrc/rltv_chain_fft.cuh): forward blur, residual and adjoint in one pass with the residual kept in
     the row-frequency domain, against the float64 definition  g = conv(conv(u, psf, 'valid') - image, rot180 psf, 'full')
     (pyx:477-491) and its own step statistics (pyx:524 with lambda = 1, ut = u).  Shapes: smaller than one segment,
-    around one segment (V = 128 - 2(K-1) columns), several segments and several 24-row steps per piece."""
+    around one segment (V = 128 - 2(K-1) columns), several segments and several 16-row steps per piece."""
     from image_cases_studies_b200.solver import Solver
     from oracle import rl_mm_oracle as orc
+    monkeypatch.setenv("RLTV_CHAIN_MINPIX", "0")      # K <= 9 take the chain kernel on megapixel frames only by default
     M, N = shape
     rng = np.random.default_rng(7000 + 100 * K + M)
     u = (0.1 + 0.8 * rng.random((M + K - 1, N + K - 1, 3))).astype(np.float32)
@@ -471,3 +472,29 @@ def test_pam_collaborative_tv_mode_against_its_definition(dc, name, scale, iters
     mm = orc.richardson_lucy_MM(c.image, c.u0, c.psf0, *c.window, c.tau, M, N, 3, c.MK, c.iterations, c.step_factor, c.lambd,
                                 blind=c.blind)
     assert rel_l2(mm.u, ref.u) > 1e-6
+
+
+@pytest.mark.parametrize("name,scale,iters", [("c5_nonblind_4k_kaiser7", 0.12, 4), ("c1_nonblind_512_g5", 0.6, 4),
+                                               ("c2_blind_2mp_k9", 0.2, 3)])
+def test_small_psf_chain_path_against_oracle(dc, name, scale, iters, monkeypatch):
+    """K = 5, 7, 9 through the chain kernel (the default on megapixel frames; forced here on small ones): non-blind K = 7
+    and K = 5 (gradient by k_chain_fft, whiteness residual by the direct forward stencil) and blind K = 9 (chain kernel +
+    fused PSF gradient), whole solves against the float64 oracle (pyx:460-656)."""
+    from image_cases_studies_b200 import synthetic
+    from oracle import rl_mm_oracle as orc
+    monkeypatch.setenv("RLTV_CHAIN_MINPIX", "0")
+    dc.clear_cache()
+    try:
+        c = synthetic.make_case(name, seed=5, scale=scale, iterations=iters)
+        M, N = c.shape
+        u, psf = c.u0.copy(), c.psf0.copy()
+        out = dc.richardson_lucy_MM(c.image, u, psf, *c.window, c.tau, M, N, 3, c.MK, c.iterations, c.step_factor, c.lambd,
+                                    blind=c.blind)
+        ref = orc.richardson_lucy_MM(c.image, c.u0, c.psf0, *c.window, c.tau, M, N, 3, c.MK, c.iterations, c.step_factor,
+                                     c.lambd, blind=c.blind)
+        assert dc.last_stats["iterations"] == ref.iterations
+        assert rel_l2(out, ref.out) <= 1e-4
+        assert psf_l1(psf, ref.psf) <= 1e-4
+        assert np.allclose(dc.last_stats["M_r_history"], ref.M_r, rtol=2e-5)
+    finally:
+        dc.clear_cache()
