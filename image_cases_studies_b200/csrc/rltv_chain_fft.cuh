@@ -1,4 +1,4 @@
-// Spectral chain kernel: forward blur, residual and adjoint of one inner step in ONE pass, 11 <= K <= 17
+// Spectral chain kernel: forward blur, residual and adjoint of one inner step in ONE pass, 5 <= K <= 17
 //   err = conv(u, psf, "valid") - image ;  g = conv(err, rot180 psf, "full")            lib/deconvolution.pyx:477-491
 //   + the step statistics max(u_c), max|lambda g + (u - ut)/2|                            pyx:519, :524
 //
@@ -9,27 +9,29 @@
 //     G^[y]   =       sum_ky W1[ky] Err^[y-P+ky]                  per solve: the image does not change)
 // so a row costs ONE forward FFT (u) and ONE inverse FFT (g) instead of four, at the price of a shorter valid span:
 // two chained circular convolutions leave V = 128 - 2(K-1) valid columns per segment (100 at K = 15).
-// Rows are processed ROLLING down a column strip in steps of S = 24 packed rows, so no vertical halo is ever
-// transformed twice; the spectra of the last 2P rows are kept for the next step.
+// Rows are processed ROLLING down a column strip in steps of S = 16 packed rows, so no vertical halo is ever
+// transformed twice; the spectra of the previous step stay in a three-deep ring for the window of the next one.
 //
 // The residual must be ZERO outside the image (the 'full' convolution of pyx:491 sees zeros there), which a product of
 // spectra cannot express.  Only the first and last segment of a row and the first / last P rows of the frame are
 // affected; those steps take a slower path that drops to the signal domain once (inverse FFT, mask, forward FFT).
 //
-// One CTA per SM, 20 warps in FIVE roles of one warp group (4 warps = one warp per SM sub-partition) each, ONE block
-// barrier per step, a five-stage software pipeline over the steps s of 16 packed rows:
-//   time t   role      works on step   reads -> writes
-//   FFT      t         TMA stage (double-buffered) -> U^ ring block s % 3              [+ the masking path for role G]
-//   E        t - 1     U^ block + last 2P rows of the previous ring block, W0, I^ (L2) -> Err^ ring block (private columns)
-//   G        t - 2     Err^ block + last 2P rows of the previous one, W1 -> G^ ring block
-//   IFFT     t - 3     G^ block, in place (row-local)
-//   EPI      t - 4     g rows (signal domain) + u / ut from L2 -> g store, step statistics
+// One CTA per SM, 24 warps in FIVE roles -- warp groups (4 warps = one warp per SM sub-partition): E, G, IFFT and FFT one
+// each, the epilogue two -- ONE block barrier per step, a five-stage software pipeline over the steps s of 16 packed rows:
+//   role     works on step   reads -> writes
+//   FFT      t               TMA stage (double-buffered) -> U^ ring block s % 3          [+ the masking path for role G]
+//   E        t - 1           U^ block + last 2P rows of the previous ring block, W0 (registers), I^ (L2) -> Err^ ring block
+//   G        t - 2           Err^ block + last 2P rows of the previous one, W1 (registers) -> G^ ring block
+//   IFFT     t - 3           G^ block, in place (row-local)
+//   EPI      t - 4           g rows (signal domain) + u / ut from L2 -> g store, step statistics   (16 threads per row pair)
+// Every role has its own register budget (setmaxnreg: E 112, G 96, FFT / IFFT 72, EPI 64 per thread; the launch has 80).
 // Round 2's first version had three roles (FFT 6 warps, MAC 4, IFFT + epilogue 6) at 24 rows per step.  ncu's source-level
 // stall samples showed the lone MAC warp of each sub-partition busy 83 % of the kernel (2 200 dependent instructions per
 // step at ~4 cycles each: it WAS the step time) and the IFFT + epilogue warps 74 % (latency chains: shared-memory round
 // trips of the FFT passes, then the L2 round trips of the epilogue operands).  Splitting both along the pipeline -- not
 // across rows, which needs barriers between the halves -- halves the serial chain of every role; three-deep rings replace
-// the tail copies.  The FMA pipe stays the bound (E and G: 960 pipe cycles per step and sub-partition each, FFT roles ~700).
+// the tail copies; the taps moved from shared memory into registers.  0.60 -> 0.50 ms at 24 MP, K = 15; the FMA pipe
+// (48 % busy) and instruction issue (51 %) are now contended by six warps per sub-partition rather than idle behind one.
 #pragma once
 #include "rltv_band.cuh"
 #include "rltv_common.cuh"

@@ -182,11 +182,11 @@ int rltv_gather_download(rltv_ctx* ctx, float* u, size_t u_row_stride_bytes);
 int rltv_stage_residual(rltv_ctx* ctx, float* err_out /* packed HWC (M,N,3) */);
 /* g = full-conv(err, rot180(psf)) on the u domain (pyx:490-491), using the residual currently on device */
 int rltv_stage_adjoint(rltv_ctx* ctx, float* g_out /* packed HWC (M+MK-1, N+MK-1, 3) */);
-/* Spectral chain kernel (11 <= MK <= 17, csrc/rltv_chain_fft.cuh): g = full-conv(valid-conv(u, psf) - image, rot180(psf))
+/* Spectral chain kernel (5 <= MK <= 17, csrc/rltv_chain_fft.cuh; default for MK >= 11, and for MK = 5, 7, 9 on megapixel frames): g = full-conv(valid-conv(u, psf) - image, rot180(psf))
  * (pyx:477-491) in one pass from u, psf and the image on the device; also returns the step statistics it reduces,
  * max(u_c) and max|g_c| per channel (pyx:524 with lambda = 1 and ut = u).  RLTV_ERR_STATE if the context does not use it. */
 int rltv_stage_chain(rltv_ctx* ctx, float* g_out /* packed HWC (M+MK-1, N+MK-1, 3) */, float* max6 /* 6 floats or NULL */);
-/* debug: skip roles of the chain kernel (bit 0 forward FFT, 1 MAC, 2 inverse FFT + epilogue, 3 TMA loads); timing only */
+/* debug: skip roles of the chain kernel (bit 0 forward FFT, 1 role E, 2 inverse FFT, 3 TMA loads, 4 role G, 5 epilogue); timing only */
 int rltv_debug_chain_roles(int32_t mask);
 /* gk = valid-conv(rot180(u), err) (pyx:567-571).  Direct kernels / MK > 17: uses the residual currently on device
  * (call rltv_stage_residual first).  Row-FFT kernels, MK <= 17: the kernel computes the residual of pyx:557-565
