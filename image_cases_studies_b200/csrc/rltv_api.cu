@@ -247,7 +247,7 @@ int make_maps_t(rltv_ctx* c) {
   }
   if constexpr (K >= 9) {
     using GF = GradkFftCfg<K>;
-    if ((rc = make_tmap(&c->tm_u_gkfft, c->u, g, g.Hu, FFT_N, GF::U_ROWS))) return rc;
+    if ((rc = make_tmap(&c->tm_u_gkfft, c->u, g, g.Hu, GF::UW, GF::U_ROWS))) return rc;
     if ((rc = make_tmap(&c->tm_err_gkfft, c->err + size_t(g.own0) * g.pitch, g, g.own1 - g.own0, FFT_N, GF::TROWS))) return rc;
     if ((rc = make_tmap(&c->tm_img_gkfft, c->img + size_t(g.own0) * g.pitch, g, g.own1 - g.own0, FFT_N, GF::TROWS))) return rc;
   }

@@ -180,6 +180,10 @@ __device__ int g_chain_skip_roles = 0;
 struct ChainCursor {   // (piece, step) of one role; advanced once per time step
   int p, j;
 };
+struct ChainPieceCursor {   // ... with the piece itself in registers (re-read only when the piece changes)
+  int p, j;
+  ChainPiece pc;
+};
 
 // ------------------------------------------------------------------------------------------------
 // The kernel.  grid = number of SMs; CTA b works through pieces [cta_first[b], cta_first[b + 1]).
@@ -238,6 +242,15 @@ k_chain_fft(const __grid_constant__ CUtensorMap tm_u, Geom g, State* __restrict_
   auto advance = [&](ChainCursor& cur) {
     if (++cur.j >= piece_nsteps(cur.p)) { cur.j = 0; ++cur.p; }
   };
+  // the MAC and epilogue roles keep their piece in registers: per step that is one compare instead of a table lookup
+  // (ncu: ~100 of a MAC role's 680-770 instructions per step were this bookkeeping)
+  auto advance_pc = [&](ChainPieceCursor& cur) {
+    if (++cur.j >= cur.pc.nsteps) {
+      cur.j = 0;
+      ++cur.p;
+      if (cur.p < p1) cur.pc = piece(cur.p);
+    }
+  };
   // a step needs the slow (masking) path if its residual rows touch rows outside the image or the segment is a border one
   auto needs_fix = [&](const ChainPiece& pc, int j) {
     const int ea = pc.ya + j * C::S - 3 * C::P, eb = ea + pc.L;
@@ -252,13 +265,14 @@ k_chain_fft(const __grid_constant__ CUtensorMap tm_u, Geom g, State* __restrict_
   constexpr int RB = C::RB;
   // Every role runs its own copy of the time loop (the register budgets differ: setmaxnreg applies to the code that
   // follows it) and meets the others at the end of every time step.
-  auto step_barrier = [&]() { named_bar_sync(0, C::THREADS); };
+  // (a NAMED barrier: the roles arrive from different places of the code, which barrier 0 = __syncthreads() must not see)
+  auto step_barrier = [&]() { named_bar_sync(5, C::THREADS); };
 
   if (role == 3) {
     // ================= FFT: masking path of role G's step t - 2, then the forward FFT of step t =================
     set_maxnreg_dec<C::REG_FFT>();
     const int zr = rt >> 3, tt = rt & 7;                  // row of the step, thread of the row
-    ChainCursor cfix{p0, 0};                              // role G's cursor
+    ChainPieceCursor cfix{p0, 0, piece(p0)};              // role G's cursor
     ChainCursor cload{p0, 0};                             // first thread: the TMA load cursor, two steps ahead
     if (rt == 0 && !(skip & 8)) {
       issue(piece(p0), 0, 0);
@@ -268,7 +282,7 @@ k_chain_fft(const __grid_constant__ CUtensorMap tm_u, Geom g, State* __restrict_
     }
     for (int t = 0; t < nt; ++t) {
       if (t >= 2 && t - 2 < total) {
-        const ChainPiece pc = piece(cfix.p);
+        const ChainPiece& pc = cfix.pc;
         if (fix_on && needs_fix(pc, cfix.j)) {
           const int rb = (t - 2) % C::RING;
           float2* scratch = GB + (rb * C::S + zr) * FFT_PITCH;       // G^ block of that step: not written yet
@@ -294,7 +308,7 @@ k_chain_fft(const __grid_constant__ CUtensorMap tm_u, Geom g, State* __restrict_
           __threadfence_block();
           named_bar_arrive(2, 2 * C::ROLE);                          // role G may read the masked Err^
         }
-        advance(cfix);
+        advance_pc(cfix);
       }
       if (t < total) {
         if (!(skip & 1)) {
@@ -326,30 +340,31 @@ k_chain_fft(const __grid_constant__ CUtensorMap tm_u, Geom g, State* __restrict_
 #pragma unroll
     for (int ky = 0; ky < K; ++ky) w[ky] = make_float2(0.f, 0.f);
     float2 iv[RB];                                        // image spectra of the thread's next block (loaded one block ahead)
+    // this role's (piece, step) with the three piece fields it needs in registers; ring blocks of the step and its predecessor
+    int ep = p0, ej = 0, e_c, e_ipk, e_ns, rb = 0, rp = C::RING - 1;
     {
-      const float2* ip = Ipk + size_t(piece(p0).ipk_row0) * FFT_N + mk;
+      const ChainPiece q = piece(p0);
+      e_c = q.c; e_ipk = q.ipk_row0; e_ns = q.nsteps;
+      const float2* ip = Ipk + size_t(e_ipk) * FFT_N + mk;
 #pragma unroll
       for (int y = 0; y < RB; ++y) iv[y] = __ldg(ip + size_t(y) * FFT_N);
     }
     for (int t = 0; t < nt; ++t) {
       if (t >= 1 && t - 1 < total) {
         if (!(skip & 2)) {
-          const int s = t - 1;
-          const ChainPiece pc = piece(cur.p);
-          if (pc.c != cur_wc) {
+          if (e_c != cur_wc) {
             // forward tap spectra of this channel, scaled by 128 (Err^ must be the unnormalised spectrum, like I^)
 #pragma unroll
             for (int ky = 0; ky < K; ++ky) {
-              const float2 v = __ldg(wspec + (size_t(pc.c) * K + ky) * FFT_N + kk);
+              const float2 v = __ldg(wspec + (size_t(e_c) * K + ky) * FFT_N + kk);
               w[ky] = make_float2(v.x * float(FFT_N), v.y * (sgn * float(FFT_N)));
             }
-            cur_wc = pc.c;
+            cur_wc = e_c;
           }
-          const int rb = s % C::RING, rp = (s + C::RING - 1) % C::RING;
           const float2* ucur = U + rb * C::S * FFT_PITCH + mk;
           const float2* uprev = U + (rp * C::S + C::S - C::T2) * FFT_PITCH + mk;
           float2* ecur = EC + rb * C::S * FFT_N + mk;
-          const float2* ip = Ipk + (size_t(pc.ipk_row0) + size_t(cur.j) * C::S) * FFT_N + mk;
+          const float2* ip = Ipk + (size_t(e_ipk) + size_t(ej) * C::S) * FFT_N + mk;
           float2 z[RB + K - 1];
 #pragma unroll
           for (int m = 0; m < C::T2; ++m) z[m] = uprev[m * FFT_PITCH];
@@ -366,16 +381,20 @@ k_chain_fft(const __grid_constant__ CUtensorMap tm_u, Geom g, State* __restrict_
 #pragma unroll
             for (int m = 0; m < C::T2; ++m) z[m] = z[m + RB];
           }
-          // image spectra of this thread's first block of the NEXT step: in flight across the barrier
-          if (t < total) {
-            ChainCursor nx = cur;
-            advance(nx);
-            const float2* ipn = Ipk + (size_t(piece(nx.p).ipk_row0) + size_t(nx.j) * C::S) * FFT_N + mk;
-#pragma unroll
-            for (int y = 0; y < RB; ++y) iv[y] = __ldg(ipn + size_t(y) * FFT_N);
-          }
         }
-        advance(cur);
+        // next step
+        if (++ej >= e_ns) {
+          ej = 0;
+          if (++ep < p1) { const ChainPiece q = piece(ep); e_c = q.c; e_ipk = q.ipk_row0; e_ns = q.nsteps; }
+        }
+        rp = rb;
+        rb = (rb == C::RING - 1) ? 0 : rb + 1;
+        // image spectra of this thread's first block of that step: in flight across the barrier
+        if (t < total && !(skip & 2)) {
+          const float2* ipn = Ipk + (size_t(e_ipk) + size_t(ej) * C::S) * FFT_N + mk;
+#pragma unroll
+          for (int y = 0; y < RB; ++y) iv[y] = __ldg(ipn + size_t(y) * FFT_N);
+        }
       }
       step_barrier();
     }
@@ -388,11 +407,12 @@ k_chain_fft(const __grid_constant__ CUtensorMap tm_u, Geom g, State* __restrict_
     float2 w[K];
 #pragma unroll
     for (int ky = 0; ky < K; ++ky) w[ky] = make_float2(0.f, 0.f);
+    ChainPieceCursor cg{p0, 0, piece(p0)};
+    int rb = 0, rp = C::RING - 1;                         // ring blocks of the step and its predecessor
     for (int t = 0; t < nt; ++t) {
       if (t >= 2 && t - 2 < total) {
         if (!(skip & 16)) {
-          const int s = t - 2;
-          const ChainPiece pc = piece(cur.p);
+          const ChainPiece& pc = cg.pc;
           if (pc.c != cur_wc) {
 #pragma unroll
             for (int ky = 0; ky < K; ++ky) {
@@ -401,8 +421,7 @@ k_chain_fft(const __grid_constant__ CUtensorMap tm_u, Geom g, State* __restrict_
             }
             cur_wc = pc.c;
           }
-          if (fix_on && needs_fix(pc, cur.j)) named_bar_sync(2, 2 * C::ROLE);   // the FFT role has masked this step's Err^
-          const int rb = s % C::RING, rp = (s + C::RING - 1) % C::RING;
+          if (fix_on && needs_fix(pc, cg.j)) named_bar_sync(2, 2 * C::ROLE);    // the FFT role has masked this step's Err^
           const float2* ecur = EC + rb * C::S * FFT_N + mk;
           const float2* eprev = EC + (rp * C::S + C::S - C::T2) * FFT_N + mk;
           float2* gb = GB + rb * C::S * FFT_PITCH + mk;
@@ -419,7 +438,9 @@ k_chain_fft(const __grid_constant__ CUtensorMap tm_u, Geom g, State* __restrict_
             for (int m = 0; m < C::T2; ++m) z[m] = z[m + RB];
           }
         }
-        advance(cur);
+        advance_pc(cg);
+        rp = rb;
+        rb = (rb == C::RING - 1) ? 0 : rb + 1;
       }
       step_barrier();
     }
@@ -445,11 +466,15 @@ k_chain_fft(const __grid_constant__ CUtensorMap tm_u, Geom g, State* __restrict_
       mG = fmaxf(mG, fabsf(fmaf(lambd, o, 0.5f * (uu - tv))));
       mu = fmaxf(mu, uu);
     };
+    ChainPieceCursor ce{p0, 0, piece(p0)};
+    int rb = 0;                                           // ring block of the step
     for (int t = 0; t < nt; ++t) {
       if (t >= 4 && t - 4 < total) {
-        const ChainPiece pc = piece(cur.p);
+        const int pc_c = ce.pc.c;
+        const bool last_of_piece = ce.j == ce.pc.nsteps - 1;
         if (!(skip & 32)) {
-          const int rel = cur.j * C::S - 4 * C::P + zr;                // g row of the first half, relative to the piece
+          const ChainPiece& pc = ce.pc;
+          const int rel = ce.j * C::S - 4 * C::P + zr;                 // g row of the first half, relative to the piece
           const bool va = rel >= 0 && rel < pc.L, vb = rel >= 0 && rel < pc.Lb;
           const int xs = C::V * pc.s;
           const size_t offa = size_t(pc.c) * g.plane + size_t(va ? pc.ya + rel : 0) * g.pitch + xs;
@@ -472,11 +497,10 @@ k_chain_fft(const __grid_constant__ CUtensorMap tm_u, Geom g, State* __restrict_
           }
           // the rows of the NEXT step into L2 (a whole time step ahead of their use): one line address per thread --
           // (array, half, line) -- the 16-byte aligned row of V floats touches four lines of 128 B, or a fifth
+          advance_pc(ce);                                              // (everything of the current step that depends on its piece is in registers by now)
           if (t - 3 < total) {
-            ChainCursor nx = cur;
-            advance(nx);
-            const ChainPiece pn = piece(nx.p);
-            const int reln = nx.j * C::S - 4 * C::P + zr;
+            const ChainPiece& pn = ce.pc;
+            const int reln = ce.j * C::S - 4 * C::P + zr;
             const int arr = tt & 1, part = (tt >> 1) & 1, ln = tt >> 2;
             const bool v = reln >= 0 && reln < (part ? pn.Lb : pn.L);
             const int xn = C::V * pn.s;
@@ -486,7 +510,7 @@ k_chain_fft(const __grid_constant__ CUtensorMap tm_u, Geom g, State* __restrict_
               if (ln == 0 && xn + C::V - 4 < g.pitch) prefetch_l2(rowp + C::V - 4);
             }
           }
-          const float2* row = GB + (((t - 4) % C::RING) * C::S + zr) * FFT_PITCH + (K - 1);
+          const float2* row = GB + (rb * C::S + zr) * FFT_PITCH + (K - 1);
           const bool full = xs + C::V <= g.Wu;                         // the segment lies inside the row: no column checks
 #pragma unroll
           for (int q = 0; q < NQ; ++q) {
@@ -525,17 +549,19 @@ k_chain_fft(const __grid_constant__ CUtensorMap tm_u, Geom g, State* __restrict_
             }
           }
           // end of a piece: flush the statistics of its channel
-          if (cur.j == pc.nsteps - 1) {
+          if (last_of_piece) {
             const float wu = warp_max(mu), wG = warp_max(mG);
             if (lane == 0) {
-              atomicMax(&st->smax[slot][pc.c], f2ord(wu));
-              atomicMax(&st->smax[slot][3 + pc.c], f2ord(wG));
+              atomicMax(&st->smax[slot][pc_c], f2ord(wu));
+              atomicMax(&st->smax[slot][3 + pc_c], f2ord(wG));
             }
             mu = -INFINITY;
             mG = 0.f;
           }
+        } else {
+          advance_pc(ce);
         }
-        advance(cur);
+        rb = (rb == C::RING - 1) ? 0 : rb + 1;
       }
       step_barrier();
     }

@@ -207,7 +207,7 @@ k_conv_fft(const __grid_constant__ CUtensorMap tm_in, const float* __restrict__ 
       const unsigned mask = __activemask();
       const int zr = task >> 3, tt = task & 7;
       float2* row = ZB + zr * FFT_PITCH;
-      fft128_row<true, C::TWB>(row, tw, tt, [&](int n) { return row[n]; }, mask);
+      fft128_core<true, C::TWB>(row, tw, tt, [&](int j) { return row[tt + 8 * j]; }, mask, 0);
     }
     __syncthreads();
     mark(3);
@@ -344,7 +344,10 @@ struct GradkFftCfg {
   static constexpr int ZU_ROWS = HB + K - 1;
   static constexpr int NCH = THREADS / FFT_N;
   static constexpr int CHUNK = HB / NCH;
-  static constexpr int U_BYTES = U_ROWS * FFT_N * 4;
+  static constexpr int UW = 136;                    // TMA box width of the u rows (floats): rows start 8 banks apart, so the four
+                                                    // rows a warp transforms read the dense buffer conflict-free at compile-time offsets
+  static constexpr int U_TX = U_ROWS * UW * 4;      // bytes of the TMA transaction
+  static constexpr int U_BYTES = (U_TX + 127) & ~127;
   static constexpr int E_BYTES = TROWS * FFT_N * 4;
   static constexpr int ZU_BYTES = ZU_ROWS * FFT_PITCH * 8;
   static constexpr int ZE_BYTES = HB * FFT_PITCH * 8;
@@ -405,7 +408,7 @@ k_gradk_fft(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
     const int f = blockIdx.x + q * gridDim.x;
     const int c = f / tiles_per_c, tl = f - c * tiles_per_c;
     const int by = tl / ntx, bx = tl - by * ntx;
-    mbar_arrive_expect_tx(bar, C::U_BYTES + C::E_BYTES);
+    mbar_arrive_expect_tx(bar, C::U_TX + C::E_BYTES);
     tma_load_3d(smem, &tm_u, bx * C::TWO - C::P4, g.own0 + by * C::TROWS - C::P, c, bar);
     tma_load_3d(smem + C::U_BYTES, &tm_e, bx * C::TWO - C::P4, by * C::TROWS, c, bar);   // tm_e: owned rows only
   };
@@ -447,9 +450,9 @@ k_gradk_fft(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
         const unsigned mask = __activemask();
         const int zr = task >> 3, tt = task & 7;
         if (zr < C::ZU_ROWS) {
-          const float* ra = uR + zr * FFT_N;
-          const float* rb = uR + (zr + C::HB) * FFT_N;
-          fft128_row<false, C::TWB>(ZU + zr * FFT_PITCH, tw, tt, [&](int n) { return make_float2(ra[n], rb[n]); }, mask, zr & 3);
+          const float* ra = uR + zr * C::UW + tt;
+          const float* rb = ra + C::HB * C::UW;
+          fft128_core<false, C::TWB>(ZU + zr * FFT_PITCH, tw, tt, [&](int j) { return make_float2(ra[8 * j], rb[8 * j]); }, mask, 0);
         } else {
           const int er = zr - C::ZU_ROWS;
           const float* ra = eR + er * FFT_N;
@@ -470,9 +473,9 @@ k_gradk_fft(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
       for (int task = tid; task < C::ZU_ROWS * 8; task += C::THREADS) {
         const unsigned mask = __activemask();
         const int zr = task >> 3, tt = task & 7;
-        const float* ra = uR + zr * FFT_N;
-        const float* rb = uR + (zr + C::HB) * FFT_N;
-        fft128_row<false, C::TWB>(ZU + zr * FFT_PITCH, tw, tt, [&](int n) { return make_float2(ra[n], rb[n]); }, mask, zr & 3);
+        const float* ra = uR + zr * C::UW + tt;
+        const float* rb = ra + C::HB * C::UW;
+        fft128_core<false, C::TWB>(ZU + zr * FFT_PITCH, tw, tt, [&](int j) { return make_float2(ra[8 * j], rb[8 * j]); }, mask, 0);
       }
       __syncthreads();
       // b. blur: O[y][bin] = sum_ky Wc[ky][bin] Zu[y + ky][bin] -> ZE row y, two half-chunks to stay within registers
@@ -503,29 +506,33 @@ k_gradk_fft(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
         const unsigned mask = __activemask();
         const int zr = task >> 3, tt = task & 7;
         float2* row = ZE + zr * FFT_PITCH;
-        fft128_row<true, C::TWB>(row, tw, tt, [&](int n) { return row[n]; }, mask);
+        fft128_core<true, C::TWB>(row, tw, tt, [&](int j) { return row[tt + 8 * j]; }, mask, 0);
       }
       __syncthreads();
-      // d. residual = blur - image inside the image and the owned rows, zero elsewhere (and in the 16 invalid columns)
+      // d. residual = blur - image inside the image and the owned rows, zero elsewhere (and in the 16 invalid columns).
+      //    A thread keeps its column (THREADS is a multiple of 128): everything that depends on the column only is
+      //    computed once per tile (ncu: written per element, this phase was 16 % of the kernel's instructions, all integer).
       {
-        const int x0 = bx * C::TWO - C::P4;
-        for (int i = tid; i < C::HB * FFT_N; i += C::THREADS) {
-          const int r = i >> 7, n = i & (FFT_N - 1);
+        static_assert(C::THREADS % FFT_N == 0, "one column per thread");
+        constexpr int RSTEP = C::THREADS / FFT_N;
+        const int n = tid & (FFT_N - 1);
+        const int X = bx * C::TWO - C::P4 + n;
+        const bool nvalid = (n >= C::P4) && (n < C::P4 + C::TWO);
+        const bool colin = nvalid && X >= C::P && X < C::P + g.N;
+        const bool store = err_out != nullptr && nvalid && X < g.pitch;
+        const int rl0 = by * C::TROWS;                             // first tile row inside the owned rows
+        const int lim = min(nown, C::P + g.M - g.row0 - g.own0);   // rows rl in [lo, lim) lie inside the image and the band
+        const int lo = C::P - g.row0 - g.own0;
+        float* eo = err_out + size_t(c) * g.plane + size_t(g.own0 + rl0) * g.pitch + X;
+#pragma unroll 2
+        for (int r = tid >> 7; r < C::HB; r += RSTEP) {
           const float2 v = ZE[r * FFT_PITCH + n];
-          const int X = x0 + n;
-          const bool nvalid = (n >= C::P4) && (n < C::P4 + C::TWO);
-          const bool colin = nvalid && X >= C::P && X < C::P + g.N;
-          float e[2];
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int rl = by * C::TROWS + r + h * C::HB;          // row inside the owned rows
-            const int gy = g.row0 + g.own0 + rl;                   // row of the padded frame
-            const bool ok = colin && rl < nown && gy >= C::P && gy < C::P + g.M;
-            e[h] = ok ? (h ? v.y : v.x) - eR[(r + h * C::HB) * FFT_N + n] : 0.f;
-            if (err_out != nullptr && nvalid && X < g.pitch && rl < nown)
-              err_out[size_t(c) * g.plane + size_t(g.own0 + rl) * g.pitch + X] = e[h];
-          }
-          ZE[r * FFT_PITCH + n] = make_float2(e[0], e[1]);
+          const int ra = rl0 + r, rb = ra + C::HB;
+          const float ea = (colin && ra >= lo && ra < lim) ? v.x - eR[r * FFT_N + n] : 0.f;
+          const float eb = (colin && rb >= lo && rb < lim) ? v.y - eR[(r + C::HB) * FFT_N + n] : 0.f;
+          if (store && ra < nown) eo[size_t(r) * g.pitch] = ea;
+          if (store && rb < nown) eo[size_t(r + C::HB) * g.pitch] = eb;
+          ZE[r * FFT_PITCH + n] = make_float2(ea, eb);
         }
       }
       __syncthreads();
@@ -535,7 +542,7 @@ k_gradk_fft(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
         const unsigned mask = __activemask();
         const int zr = task >> 3, tt = task & 7;
         float2* row = ZE + zr * FFT_PITCH;
-        fft128_row<false, C::TWB>(row, tw, tt, [&](int n) { return row[n]; }, mask);
+        fft128_core<false, C::TWB>(row, tw, tt, [&](int j) { return row[tt + 8 * j]; }, mask, 0);
       }
       __syncthreads();
     }
