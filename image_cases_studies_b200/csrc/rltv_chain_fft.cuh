@@ -261,7 +261,6 @@ k_chain_fft(const __grid_constant__ CUtensorMap tm_u, Geom g, State* __restrict_
   const int skip = g_chain_skip_roles;
   const bool fix_on = !(skip & (1 | 16));
   const int total = total_steps, nt = total_steps + C::DEPTH;
-  ChainCursor cur{p0, 0};           // this role's own (piece, step)
   constexpr int RB = C::RB;
   // Every role runs its own copy of the time loop (the register budgets differ: setmaxnreg applies to the code that
   // follows it) and meets the others at the end of every time step.
@@ -274,6 +273,9 @@ k_chain_fft(const __grid_constant__ CUtensorMap tm_u, Geom g, State* __restrict_
     const int zr = rt >> 3, tt = rt & 7;                  // row of the step, thread of the row
     ChainPieceCursor cfix{p0, 0, piece(p0)};              // role G's cursor
     ChainCursor cload{p0, 0};                             // first thread: the TMA load cursor, two steps ahead
+    int fp = p0, fj = 0, f_ipk, f_ns;                     // this role's own (piece, step): only the image-spectra row is needed
+    { const ChainPiece q = piece(p0); f_ipk = q.ipk_row0; f_ns = q.nsteps; }
+    int rbu = 0, rbf = 0;                                 // ring blocks of step t (U^) and of step t - 2 (Err^ / G^)
     if (rt == 0 && !(skip & 8)) {
       issue(piece(p0), 0, 0);
       advance(cload);
@@ -284,9 +286,8 @@ k_chain_fft(const __grid_constant__ CUtensorMap tm_u, Geom g, State* __restrict_
       if (t >= 2 && t - 2 < total) {
         const ChainPiece& pc = cfix.pc;
         if (fix_on && needs_fix(pc, cfix.j)) {
-          const int rb = (t - 2) % C::RING;
-          float2* scratch = GB + (rb * C::S + zr) * FFT_PITCH;       // G^ block of that step: not written yet
-          float2* erow = EC + (rb * C::S + zr) * FFT_N;
+          float2* scratch = GB + (rbf * C::S + zr) * FFT_PITCH;      // G^ block of that step: not written yet
+          float2* erow = EC + (rbf * C::S + zr) * FFT_N;
           fft128_core<true, true>(scratch, tw, tt, [&](int j) { return erow[tt + 8 * j]; }, 0xffffffffu, 0);
           __syncwarp();
           const int ea = pc.ya + cfix.j * C::S - 3 * C::P + zr, eb = ea + pc.L;
@@ -309,19 +310,22 @@ k_chain_fft(const __grid_constant__ CUtensorMap tm_u, Geom g, State* __restrict_
           named_bar_arrive(2, 2 * C::ROLE);                          // role G may read the masked Err^
         }
         advance_pc(cfix);
+        rbf = (rbf == C::RING - 1) ? 0 : rbf + 1;
       }
       if (t < total) {
         if (!(skip & 1)) {
-          {   // role E reads the image spectra of this step during the NEXT time step: bring them into L2 now
-            const ChainPiece pf = piece(cur.p);
-            prefetch_l2(Ipk + (size_t(pf.ipk_row0) + size_t(cur.j) * C::S) * FFT_N + rt * 16);
-          }
+          // role E reads the image spectra of this step during the NEXT time step: bring them into L2 now
+          prefetch_l2(Ipk + (size_t(f_ipk) + size_t(fj) * C::S) * FFT_N + rt * 16);
           if (!(skip & 8)) mbar_wait(bar + (t & 1), (t >> 1) & 1);
           const float* ra = reinterpret_cast<const float*>(smem + C::OFF_IN + (t & 1) * C::IN_STAGE) + zr * C::INW + C::DX + tt;
-          float2* dst = U + ((t % C::RING) * C::S + zr) * FFT_PITCH;
+          float2* dst = U + (rbu * C::S + zr) * FFT_PITCH;
           fft128_core<false, true>(dst, tw, tt, [&](int j) { return make_float2(ra[8 * j], ra[C::S * C::INW + 8 * j]); }, 0xffffffffu, 0);
         }
-        advance(cur);
+        if (++fj >= f_ns) {
+          fj = 0;
+          if (++fp < p1) { const ChainPiece q = piece(fp); f_ipk = q.ipk_row0; f_ns = q.nsteps; }
+        }
+        rbu = (rbu == C::RING - 1) ? 0 : rbu + 1;
       }
       step_barrier();
       // the TMA stage t & 1 was consumed by the forward FFT of step t: load step t + 2 into it
@@ -341,6 +345,7 @@ k_chain_fft(const __grid_constant__ CUtensorMap tm_u, Geom g, State* __restrict_
     for (int ky = 0; ky < K; ++ky) w[ky] = make_float2(0.f, 0.f);
     float2 iv[RB];                                        // image spectra of the thread's next block (loaded one block ahead)
     // this role's (piece, step) with the three piece fields it needs in registers; ring blocks of the step and its predecessor
+    // (carrying the window in registers from step to step instead of re-reading its first 2P rows: no gain, 16 B of spills)
     int ep = p0, ej = 0, e_c, e_ipk, e_ns, rb = 0, rp = C::RING - 1;
     {
       const ChainPiece q = piece(p0);
@@ -389,7 +394,8 @@ k_chain_fft(const __grid_constant__ CUtensorMap tm_u, Geom g, State* __restrict_
         }
         rp = rb;
         rb = (rb == C::RING - 1) ? 0 : rb + 1;
-        // image spectra of this thread's first block of that step: in flight across the barrier
+        // image spectra of this thread's first block of that step, issued before the barrier (measured against issuing
+        // them at the start of the step: 0.455 vs 0.460 ms)
         if (t < total && !(skip & 2)) {
           const float2* ipn = Ipk + (size_t(e_ipk) + size_t(ej) * C::S) * FFT_N + mk;
 #pragma unroll
@@ -448,10 +454,14 @@ k_chain_fft(const __grid_constant__ CUtensorMap tm_u, Geom g, State* __restrict_
     // ================= inverse FFT of the g rows of step t - 3, in place =================
     set_maxnreg_dec<C::REG_FFT>();
     const int zr = rt >> 3, tt = rt & 7;
+    int rb = 0;
     for (int t = 0; t < nt; ++t) {
-      if (t >= 3 && t - 3 < total && !(skip & 4)) {
-        float2* row = GB + (((t - 3) % C::RING) * C::S + zr) * FFT_PITCH;
-        fft128_core<true, true>(row, tw, tt, [&](int j) { return row[tt + 8 * j]; }, 0xffffffffu, 0);
+      if (t >= 3 && t - 3 < total) {
+        if (!(skip & 4)) {
+          float2* row = GB + (rb * C::S + zr) * FFT_PITCH;
+          fft128_core<true, true>(row, tw, tt, [&](int j) { return row[tt + 8 * j]; }, 0xffffffffu, 0);
+        }
+        rb = (rb == C::RING - 1) ? 0 : rb + 1;
       }
       step_barrier();
     }
