@@ -345,7 +345,10 @@ k_chain_fft(const __grid_constant__ CUtensorMap tm_u, Geom g, State* __restrict_
     for (int ky = 0; ky < K; ++ky) w[ky] = make_float2(0.f, 0.f);
     float2 iv[RB];                                        // image spectra of the thread's next block (loaded one block ahead)
     // this role's (piece, step) with the three piece fields it needs in registers; ring blocks of the step and its predecessor
-    // (carrying the window in registers from step to step instead of re-reading its first 2P rows: no gain, 16 B of spills)
+    // (measured and dropped: carrying the window in registers from step to step instead of re-reading its first 2P rows
+    //  -- no gain, 16 B of spills; the subtraction of I^ as a sixth pipeline stage run by the IFFT role, which idles 63 % of
+    //  the time -- the extra pass over the Err^ block costs more shared-memory traffic than it takes off this role,
+    //  0.454 -> 0.498 ms; the FFT twiddles of the IFFT role in registers for the whole kernel -- no change)
     int ep = p0, ej = 0, e_c, e_ipk, e_ns, rb = 0, rp = C::RING - 1;
     {
       const ChainPiece q = piece(p0);

@@ -509,6 +509,9 @@ k_gradk_fft(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
         fft128_core<true, C::TWB>(row, tw, tt, [&](int j) { return row[tt + 8 * j]; }, mask, 0);
       }
       __syncthreads();
+      // (c, d and e are all row-local; merged into one phase without block barriers -- each 8-thread group doing inverse FFT,
+      //  residual and forward FFT of its row back to back -- they are SLOWER, 0.528 vs 0.503 ms: only 320 of the 512 threads
+      //  have a row, and the reload of the real-data stage can then start only after all three)
       // d. residual = blur - image inside the image and the owned rows, zero elsewhere (and in the 16 invalid columns).
       //    A thread keeps its column (THREADS is a multiple of 128): everything that depends on the column only is
       //    computed once per tile (ncu: written per element, this phase was 16 % of the kernel's instructions, all integer).
