@@ -34,6 +34,37 @@ def test_plan_bands_properties(M, MK, world):
     assert olo <= wt and wb <= ohi                              # the window sits inside the owner's owned rows
 
 
+@pytest.mark.parametrize("M,MK,world", [(4000, 15, 2), (4000, 15, 4), (4000, 15, 8), (6336, 31, 8), (1080, 9, 4), (2160, 7, 8)])
+def test_plan_bands_balances_around_a_centred_window(M, MK, world):
+    """The default 255-px whiteness window sits in the middle of the frame, i.e. on an even cut for every even world size.
+    Its rows must all belong to one band; the cuts then minimise the LARGEST band (every kernel of every step waits for
+    that band): no band may exceed what the constraint itself forces."""
+    P, Hu = MK // 2, M + MK - 1
+    top = M // 2 - 128
+    window = (top, top + 255, 10, 265)
+    bands, owner = plan_bands(M, MK, world, window)
+    sizes = [b[3] - b[2] for b in bands]
+    assert sum(sizes) == Hu and bands[0][2] == 0 and bands[-1][3] == Hu
+    wt, wb = window[0] + P, window[1] + P
+    assert bands[owner][2] <= wt and wb <= bands[owner][3]
+    # lower bound on the largest band: the even share, or -- if the window forces the owner to start at 0 / end at Hu or
+    # to span more than a share -- whatever the best owner position k leaves; brute force over all (k, a, b)
+    best = Hu
+    for k in range(world):
+        for T in range(-(-Hu // world), Hu + 1):
+            a = 0 if k == 0 else min(wt, k * T)
+            b = Hu if k == world - 1 else max(wb, Hu - (world - 1 - k) * T)
+            if a <= wt and b >= wb and b - a <= T and a >= 2 * P * k and Hu - b >= 2 * P * (world - 1 - k):
+                best = min(best, T)
+                break
+    assert max(sizes) <= best + 1, (sizes, best)
+    # and it is never worse than moving only the one cut below the window (what the first version did)
+    even = [round(i * Hu / world) for i in range(world + 1)]
+    o = max(i for i in range(world) if even[i] <= wt)
+    naive = max(wb - even[o], *(even[i + 1] - even[i] for i in range(o))) if o else wb - even[o]
+    assert max(sizes) <= max(naive, -(-Hu // world) + 1)
+
+
 def test_plan_bands_rejects_too_many_gpus():
     with pytest.raises(ValueError):
         plan_bands(40, 15, 8, None)
