@@ -67,8 +67,10 @@ def test_committed_ncu_traffic_is_readable(family):
         none, _ = bench.ncu_traffic("c1_nonblind_512_g5", family)
     finally:
         sys.path.pop(0)
-    # hundreds of MB per launch on the 24 MP frame -- or nothing at all when the capture predates the current kernels
-    assert (val and val > 1e8 and "profiles/" in src) or (val is None and "stale" in (src or "stale"))
+    # hundreds of MB per launch on the 24 MP frame -- or nothing at all when the capture predates the current kernels, or
+    # when the family does not launch on this workload (the chain kernel does the forward blur inside "conv_adj")
+    assert (val and val > 1e8 and "profiles/" in src) or (val is None and "stale" in (src or "stale")) \
+        or (val is None and family == "conv_fwd" and "profiles/" in src)
     assert none is None                                  # no capture for other workloads: traffic stays null
 
 
